@@ -1,0 +1,28 @@
+"""b200wave: the B200-native (sm_100a) wavelet + SSIM hot path of
+KevynUtopia/Frequency-Aware-Inverse-Consistent-OCTA-Super-Resolution.
+
+Drop-in surface (same names and signatures as the reference):
+
+* ``DWTForward``, ``DWTInverse`` and the aliases ``DWT``, ``IDWT``, ``DWT2D``, ``IDWT2D``
+  (``pytorch_wavelets/__init__.py:24-33``), ``dwt.lowlevel.AFB2D`` / ``SFB2D`` / ``afb2d`` / ``sfb2d``
+* ``SSIM``, ``ssim`` (``ssim.py``)
+
+Everything computes in hand-written CUDA kernels behind ``torch.ops.b200wave``;
+there is no CPU path.
+"""
+from . import ops  # noqa: F401  (registers torch.ops.b200wave.*)
+from . import dwt  # noqa: F401
+from .dwt import lowlevel  # noqa: F401
+from .dwt.transform2d import DWTForward, DWTInverse
+from .ssim import SSIM, ssim
+from .wavelets import Wavelet, wavelist  # noqa: F401
+
+__version__ = "0.1.0"
+
+DWT = DWTForward
+IDWT = DWTInverse
+DWT2D = DWT
+IDWT2D = IDWT
+
+__all__ = ["DWTForward", "DWTInverse", "DWT", "IDWT", "DWT2D", "IDWT2D", "SSIM", "ssim", "lowlevel",
+           "Wavelet", "wavelist", "__version__"]

@@ -1,0 +1,94 @@
+"""Build ``libb200wave.so`` in-tree with nvcc for sm_100a.
+
+    python -m b200wave._build            (or ``__graft_entry__.build()``)
+
+The library is a plain C-ABI shared object (``include/b200wave.h``): no torch
+headers, no pybind -- the Python side binds it with ctypes.  cudart is linked
+statically so the ``.so`` loads on a box without a toolkit on the loader path
+(and on the GPU-less build container for the symbol-export test).
+"""
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG_DIR)
+CSRC = os.path.join(PKG_DIR, "csrc")
+INCLUDE = os.path.join(ROOT, "include")
+LIB_DIR = os.path.join(PKG_DIR, "_lib")
+LIB_PATH = os.path.join(LIB_DIR, "libb200wave.so")
+STAMP = os.path.join(LIB_DIR, "libb200wave.stamp")
+
+SOURCES = ["api.cu", "dwt.cu", "ssim.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O3",
+    "-cudart", "static",
+]
+
+
+def find_nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    return None
+
+
+def _source_hash():
+    h = hashlib.sha256()
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
+    files += [os.path.join(INCLUDE, f) for f in sorted(os.listdir(INCLUDE))]
+    for f in files:
+        with open(f, "rb") as fh:
+            h.update(f.encode())
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def is_fresh():
+    if not (os.path.exists(LIB_PATH) and os.path.exists(STAMP)):
+        return False
+    with open(STAMP) as fh:
+        return fh.read().strip() == _source_hash()
+
+
+def build(force=False, verbose=False):
+    """Compile every ``csrc/*.cu`` into ``_lib/libb200wave.so``; returns its path."""
+    if not force and is_fresh():
+        return LIB_PATH
+    nvcc = find_nvcc()
+    if nvcc is None:
+        raise RuntimeError("nvcc not found: cannot build libb200wave.so (set NVCC=/path/to/nvcc)")
+    os.makedirs(LIB_DIR, exist_ok=True)
+    objs = []
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd), file=sys.stderr)
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for src, pr in procs:
+        out, _ = pr.communicate()
+        if verbose and out:
+            print(out, file=sys.stderr)
+        if pr.returncode != 0:
+            raise RuntimeError("nvcc failed on %s:\n%s" % (src, out))
+    link = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
+            "-Xcompiler", "-fPIC", "-o", LIB_PATH] + objs
+    res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("link failed:\n%s" % res.stdout)
+    with open(STAMP, "w") as fh:
+        fh.write(_source_hash())
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,107 @@
+"""ctypes binding of ``libb200wave.so`` (the C ABI declared in ``include/b200wave.h``).
+
+There is no CPU path: if the library cannot be loaded the first compute call
+raises ``RuntimeError`` -- it never falls back to torch ops or to the oracle.
+"""
+import ctypes
+import os
+import threading
+
+from . import _build
+
+_c_float_p = ctypes.POINTER(ctypes.c_float)
+
+# status codes of include/b200wave.h
+OK = 0
+ERR_BAD_MODE = -1
+ERR_BAD_TAPS = -2
+ERR_NULL_POINTER = -3
+ERR_BAD_SHAPE = -4
+ERR_REFLECT_PAD = -5
+ERR_PER_TOO_SHORT = -6
+ERR_LAUNCH = -7
+ERR_WORKSPACE = -8
+ERR_BAD_WINDOW = -9
+
+ABI_VERSION = 1
+MAX_TAPS = 64
+SSIM_MAX_WINDOW = 11
+
+# every symbol the header declares: name -> (restype, argtypes)
+_vp, _i, _i64, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t
+SYMBOLS = {
+    "b200w_abi_version": (_i, []),
+    "b200w_status_string": (ctypes.c_char_p, [_i]),
+    "b200w_last_cuda_error": (_i, []),
+    "b200w_dwt_coeff_len": (_i, [_i, _i, _i]),
+    "b200w_idwt_len": (_i, [_i, _i, _i]),
+    "b200w_afb2d_f32": (_i, [_vp, _i64, _i64, _i, _i, _i,
+                             _c_float_p, _c_float_p, _i, _c_float_p, _c_float_p, _i,
+                             _i, _vp, _vp, _vp]),
+    "b200w_sfb2d_f32": (_i, [_vp, _i64, _i64, _vp, _i, _i, _i,
+                             _c_float_p, _c_float_p, _i, _c_float_p, _c_float_p, _i,
+                             _i, _vp, _i, _i, _vp]),
+    "b200w_ssim_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "b200w_ssim_fwd_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _c_float_p, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "b200w_ssim_bwd_f32": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _c_float_p, _i, _i, _vp, _vp, _vp]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+class B200WaveError(RuntimeError):
+    pass
+
+
+def library_path():
+    return os.environ.get("B200W_LIBRARY", _build.LIB_PATH)
+
+
+def load(build_if_missing=True):
+    """Load (building first if the in-tree .so is missing or stale and nvcc exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = library_path()
+        if path == _build.LIB_PATH and build_if_missing and not _build.is_fresh():
+            if _build.find_nvcc() is not None:
+                _build.build()
+        if not os.path.exists(path):
+            raise B200WaveError(
+                "libb200wave.so not found at %s and nvcc is unavailable to build it. This package has no "
+                "CPU or PyTorch fallback: run `python __graft_entry__.py build` on a machine with CUDA 12.9." % path)
+        lib = ctypes.CDLL(path)
+        for name, (restype, argtypes) in SYMBOLS.items():
+            fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+            fn.restype = restype
+            fn.argtypes = argtypes
+        if lib.b200w_abi_version() != ABI_VERSION:
+            raise B200WaveError("libb200wave ABI version %d != expected %d" % (lib.b200w_abi_version(), ABI_VERSION))
+        _lib = lib
+    return _lib
+
+
+def status_string(code):
+    return load().b200w_status_string(int(code)).decode()
+
+
+def taps_array(values):
+    vals = [float(v) for v in values]
+    return (ctypes.c_float * len(vals))(*vals), len(vals)
+
+
+def check(code, mode_name=None):
+    """Map a negative status onto the reference's exception types."""
+    if code == OK:
+        return
+    if code == ERR_BAD_MODE:
+        # pw/dwt/lowlevel.py:88,170,269,290 raise exactly this text
+        raise ValueError("Unkown pad type: {}".format(mode_name))
+    msg = status_string(code)
+    if code == ERR_LAUNCH:
+        msg += " (cudaError %d)" % load().b200w_last_cuda_error()
+    raise B200WaveError("b200wave: " + msg)

@@ -1,0 +1,30 @@
+// ABI bookkeeping: version, status names, last CUDA error (thread-local, diagnostics only).
+#include "common.cuh"
+
+namespace b200w {
+static thread_local int g_last_cuda_error = 0;
+int set_last_cuda_error(cudaError_t e) {
+    g_last_cuda_error = (int)e;
+    return B200W_ERR_LAUNCH;
+}
+}  // namespace b200w
+
+extern "C" int b200w_abi_version(void) { return B200W_ABI_VERSION; }
+
+extern "C" int b200w_last_cuda_error(void) { return b200w::g_last_cuda_error; }
+
+extern "C" const char* b200w_status_string(int status) {
+    switch (status) {
+        case B200W_OK: return "ok";
+        case B200W_ERR_BAD_MODE: return "Unkown pad type";
+        case B200W_ERR_BAD_TAPS: return "bad filter taps (null, empty or more than B200W_MAX_TAPS)";
+        case B200W_ERR_NULL_POINTER: return "null pointer";
+        case B200W_ERR_BAD_SHAPE: return "bad shape";
+        case B200W_ERR_REFLECT_PAD: return "reflect padding must be smaller than the padded dimension";
+        case B200W_ERR_PER_TOO_SHORT: return "periodization needs a signal at least as long as the filter";
+        case B200W_ERR_LAUNCH: return "CUDA launch failed";
+        case B200W_ERR_WORKSPACE: return "workspace missing or too small";
+        case B200W_ERR_BAD_WINDOW: return "SSIM window size must be odd and at most 11";
+        default: return "unknown status";
+    }
+}

@@ -1,0 +1,73 @@
+// Shared device/host helpers for the b200wave kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "b200wave.h"
+
+namespace b200w {
+
+constexpr int kMaxTaps = B200W_MAX_TAPS;
+constexpr int kThreads = 256;
+
+// Filter taps travel by value in the kernel parameter block (constant bank): with the tap loops
+// fully unrolled every FFMA takes its coefficient as a c[0x0][..] operand, no load instruction.
+struct Taps {
+    float w_lo[kMaxTaps];  // along W
+    float w_hi[kMaxTaps];
+    float h_lo[kMaxTaps];  // along H
+    float h_hi[kMaxTaps];
+};
+
+// Extension index maps of mypad (pw/dwt/lowlevel.py:28-88) and of the periodization branch of
+// afb1d (:134-150), folded into one function: returns the source index in [0,n) or -1 for "zero".
+__device__ __forceinline__ int ext_index(int s, int n, int mode) {
+    if ((unsigned)s < (unsigned)n) return s;
+    switch (mode) {
+        case B200W_MODE_SYMMETRIC: {  // half-sample symmetric, period 2n (utils.reflect(-0.5, n-0.5))
+            int p = 2 * n;
+            int m = s % p;
+            if (m < 0) m += p;
+            return m < n ? m : p - 1 - m;
+        }
+        case B200W_MODE_REFLECT: {  // whole-sample, period 2n-2 (F.pad reflect)
+            if (n == 1) return 0;
+            int p = 2 * n - 2;
+            int m = s % p;
+            if (m < 0) m += p;
+            return m < n ? m : p - m;
+        }
+        case B200W_MODE_PERIODIC: {
+            int m = s % n;
+            if (m < 0) m += n;
+            return m;
+        }
+        case B200W_MODE_PERIODIZATION: {  // odd n: last sample repeated once, then period n+1
+            int p = n + (n & 1);
+            int m = s % p;
+            if (m < 0) m += p;
+            return m < n ? m : n - 1;
+        }
+        default:
+            return -1;  // zero
+    }
+}
+
+// index of a coefficient for the synthesis bank: outside [0,m) is zero, except for periodization
+// where the coefficient sequence is m-periodic (the wrap-add + roll of sfb1d, :252-261)
+__device__ __forceinline__ int coef_index(int k, int m, bool periodic) {
+    if ((unsigned)k < (unsigned)m) return k;
+    if (!periodic) return -1;
+    int r = k % m;
+    if (r < 0) r += m;
+    return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+int set_last_cuda_error(cudaError_t e);
+
+}  // namespace b200w

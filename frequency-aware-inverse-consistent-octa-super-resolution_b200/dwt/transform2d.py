@@ -1,0 +1,86 @@
+"""``DWTForward`` / ``DWTInverse`` -- drop-in for ``pytorch_wavelets.dwt.transform2d``.
+
+Same constructor arguments and defaults, same registered buffer names and shapes
+(``h0_col, h1_col (1,1,L,1)``, ``h0_row, h1_row (1,1,1,L)``; ``g*`` likewise) so
+``state_dict``s of the reference's ``FS_Discriminator*`` (``model.py:140,190``)
+stay loadable, same ``(yl, [yh_1 (finest) .. yh_J])`` output structure
+(``pw/dwt/transform2d.py:7-148``).  Every level is one fused sm_100a kernel.
+"""
+import torch
+import torch.nn as nn
+
+from . import lowlevel
+from ..wavelets import as_wavelet, is_wavelet
+
+
+def _filters_from(wave, attrs):
+    """``wave`` -> (col_lo, col_hi, row_lo, row_hi) raw taps, like pw/dwt/transform2d.py:22-33."""
+    if isinstance(wave, str):
+        wave = as_wavelet(wave)
+    if is_wavelet(wave):
+        lo, hi = getattr(wave, attrs[0]), getattr(wave, attrs[1])
+        return lo, hi, lo, hi
+    if len(wave) == 2:
+        return wave[0], wave[1], wave[0], wave[1]
+    if len(wave) == 4:
+        return wave[0], wave[1], wave[2], wave[3]
+    raise ValueError("wave must be a name, a Wavelet, or a tuple of 2 or 4 filters")
+
+
+class DWTForward(nn.Module):
+    """2-D DWT decomposition of an image batch.
+
+    Args:
+        J (int): number of levels.
+        wave (str | Wavelet | tuple(ndarray)): wavelet name, an object with ``dec_lo``/``dec_hi``
+            (e.g. ``pywt.Wavelet``), or ``(h0, h1)`` / ``(h0_col, h1_col, h0_row, h1_row)`` arrays.
+        mode (str): 'zero', 'symmetric', 'reflect', 'periodic' or 'periodization'.
+    """
+
+    def __init__(self, J=1, wave='db1', mode='zero'):
+        super().__init__()
+        filts = lowlevel.prep_filt_afb2d(*_filters_from(wave, ('dec_lo', 'dec_hi')))
+        for name, f in zip(('h0_col', 'h1_col', 'h0_row', 'h1_row'), filts):
+            self.register_buffer(name, f)
+        self.J = J
+        self.mode = mode
+
+    def forward(self, x):
+        """x: (N, C, H, W) -> (yl, yh); yl (N, C, H', W'), yh[j] (N, C, 3, H'', W'') holding LH, HL, HH,
+        finest scale first."""
+        mode = lowlevel.mode_to_int(self.mode)
+        yh = []
+        ll = x
+        for _ in range(self.J):
+            # NB the *_col buffers go into AFB2D's *_row slots, exactly as pw/dwt/transform2d.py:70-71
+            # does: the "col" filters therefore run along W and the "row" filters along H.
+            ll, high = lowlevel.AFB2D.apply(ll, self.h0_col, self.h1_col, self.h0_row, self.h1_row, mode)
+            yh.append(high)
+        return ll, yh
+
+
+class DWTInverse(nn.Module):
+    """2-D inverse DWT; ``forward((yl, yh))`` reconstructs the image.  ``None`` entries of ``yh`` count as
+    zeros (no zero tensor is materialised: the kernel skips the three detail bands)."""
+
+    def __init__(self, wave='db1', mode='zero'):
+        super().__init__()
+        filts = lowlevel.prep_filt_sfb2d(*_filters_from(wave, ('rec_lo', 'rec_hi')))
+        for name, f in zip(('g0_col', 'g1_col', 'g0_row', 'g1_row'), filts):
+            self.register_buffer(name, f)
+        self.mode = mode
+
+    def forward(self, coeffs):
+        yl, yh = coeffs
+        mode = lowlevel.mode_to_int(self.mode)
+        ll = yl
+        for h in yh[::-1]:
+            if h is not None:
+                # 'unpad': a level reconstructed from an odd-sized input is one sample too large
+                # (pw/dwt/transform2d.py:141-145); the crop is a view, the kernel reads it strided
+                if ll.shape[-2] > h.shape[-2]:
+                    ll = ll[..., :-1, :]
+                if ll.shape[-1] > h.shape[-1]:
+                    ll = ll[..., :-1]
+            ll = lowlevel.SFB2D.apply(ll, h, self.g0_col, self.g1_col, self.g0_row, self.g1_row, mode)
+        return ll

@@ -1,0 +1,53 @@
+"""Multi-GPU use of the hot path: plain batch sharding, one process per GPU.
+
+Every (n, c) image plane is independent in the DWT / IDWT (depthwise filtering,
+``groups=C`` at ``pw/dwt/lowlevel.py:143,164,253``) and in SSIM up to the final
+mean, so ranks take contiguous slices of the batch and the data path needs NO
+collective.  The only exchange is the scalar SSIM mean (and, in a training step,
+DDP's gradient all-reduce, which is outside this package).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n, rank, world_size):
+    """Contiguous, balanced slice [lo, hi) of ``n`` items for ``rank`` (earlier ranks get the remainder)."""
+    if world_size < 1 or not 0 <= rank < world_size:
+        raise ValueError("bad rank/world_size: %r/%r" % (rank, world_size))
+    base, rem = divmod(n, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(x, rank=None, world_size=None):
+    """This rank's slice of a batch-first tensor."""
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world_size is None:
+        world_size = dist.get_world_size() if dist.is_initialized() else 1
+    lo, hi = shard_range(x.shape[0], rank, world_size)
+    return x[lo:hi]
+
+
+def global_mean(local_mean, local_count, group=None):
+    """Mean over all ranks of per-rank means weighted by their element counts (ragged shards allowed).
+    Differentiable w.r.t. ``local_mean``: d global / d local_mean = local_count / total_count, which is
+    what sharding a ``size_average=True`` SSIM loss requires.  One all-reduce of 2 floats."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local_mean
+    with torch.no_grad():
+        buf = torch.stack([local_mean.detach().double() * float(local_count),
+                           torch.tensor(float(local_count), dtype=torch.float64, device=local_mean.device)])
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+        total_sum, total_count = buf[0], buf[1]
+        value = (total_sum / total_count).to(local_mean.dtype)
+    # value carries the global number; the gradient flows through the local term only
+    weight = float(local_count) / float(total_count.item())
+    return value.detach() + (local_mean - local_mean.detach()) * weight
+
+
+def sharded_ssim(ssim_module, img1, img2, group=None):
+    """``size_average=True`` SSIM over a batch that is sharded across ranks: each rank evaluates its
+    shard with the fused kernel, then the scalar means are combined."""
+    local = ssim_module(img1, img2)
+    return global_mean(local, img1.numel(), group=group)

@@ -1,0 +1,134 @@
+/*
+ * b200wave -- C ABI of the B200-native (sm_100a) wavelet + SSIM hot path.
+ *
+ * The reference (KevynUtopia/Frequency-Aware-Inverse-Consistent-OCTA-Super-Resolution)
+ * is pure Python and has no FFI seam of its own: the drop-in boundary is the pair of
+ * torch.autograd Functions AFB2D / SFB2D and the free function _ssim.  Each entry
+ * point below replaces the body of one of them; citations are relative to
+ * /root/reference (pw = pytorch_wavelets/pytorch_wavelets):
+ *
+ *   b200w_afb2d_f32     pw/dwt/lowlevel.py:336-347  AFB2D.forward (afb1d dim=3 then dim=2, :91-172)
+ *                       pw/dwt/lowlevel.py:682-694  SFB2D.backward (same arithmetic, synthesis taps as correlators)
+ *   b200w_sfb2d_f32     pw/dwt/lowlevel.py:671-680  SFB2D.forward (sfb1d x3, :226-271)
+ *                       pw/dwt/lowlevel.py:349-365  AFB2D.backward (same arithmetic + crop to the input H, W)
+ *   b200w_ssim_fwd_f32  ssim.py:17-37               _ssim (five 11x11 Gaussian blurs, SSIM map, mean)
+ *   b200w_ssim_bwd_f32  autograd through ssim.py:17-37 (closed form)
+ *   b200w_dwt_coeff_len pywt.dwt_coeff_len as called at pw/dwt/lowlevel.py:153
+ *
+ * Conventions
+ *   - every image pointer is DEVICE memory owned by the caller (torch); the library never
+ *     allocates or frees device memory and keeps no mutable global state => re-entrant.
+ *   - filter taps are HOST pointers (<= B200W_MAX_TAPS floats each); they are copied into
+ *     the kernel parameter block, so the call is asynchronous and CUDA-graph capturable.
+ *     Analysis taps are the correlation kernels exactly as the reference's module buffers
+ *     hold them (already time-reversed by prep_filt_afb1d, pw/dwt/lowlevel.py:970-971);
+ *     synthesis taps are as-is (prep_filt_sfb1d, :918-922).
+ *   - "w_*" taps filter along W (dim 3: the h*_row / g*_row *parameters* of AFB2D/SFB2D.forward),
+ *     "h_*" taps along H (dim 2).
+ *   - layout: fp32, planes = N*C images of H x W, unit stride along W.  Inputs take explicit
+ *     plane / row strides (in elements) so a cropped view (transform2d.py:141-145) needs no copy;
+ *     outputs are dense (the reference returns contiguous tensors, tests/test_dwt.py:47-50).
+ *   - `stream` is a cudaStream_t (NULL = legacy default stream).  Nothing synchronises.
+ *   - return value: B200W_OK (0) or a negative b200w_status; b200w_status_string() names it.
+ *     An unsupported padding mode returns B200W_ERR_BAD_MODE, which the Python wrapper raises
+ *     as ValueError("Unkown pad type: ...") like pw/dwt/lowlevel.py:88,170,290.
+ */
+#ifndef B200WAVE_H_
+#define B200WAVE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200W_ABI_VERSION 1
+#define B200W_MAX_TAPS 64
+
+/* mode_to_int, pw/dwt/lowlevel.py:274-290 */
+enum b200w_mode {
+    B200W_MODE_ZERO = 0,
+    B200W_MODE_SYMMETRIC = 1,
+    B200W_MODE_PERIODIZATION = 2,
+    B200W_MODE_CONSTANT = 3,   /* accepted by mode_to_int, rejected by afb1d/sfb1d: BAD_MODE */
+    B200W_MODE_REFLECT = 4,
+    B200W_MODE_REPLICATE = 5,  /* idem */
+    B200W_MODE_PERIODIC = 6
+};
+
+enum b200w_status {
+    B200W_OK = 0,
+    B200W_ERR_BAD_MODE = -1,      /* "Unkown pad type" */
+    B200W_ERR_BAD_TAPS = -2,      /* tap count < 1 or > B200W_MAX_TAPS, or null tap pointer */
+    B200W_ERR_NULL_POINTER = -3,
+    B200W_ERR_BAD_SHAPE = -4,     /* non-positive dimension, or out_h/out_w larger than the synthesis output */
+    B200W_ERR_REFLECT_PAD = -5,   /* reflect padding needs pad < dimension (torch F.pad rule) */
+    B200W_ERR_PER_TOO_SHORT = -6, /* periodization needs (even-extended) length >= tap count */
+    B200W_ERR_LAUNCH = -7,        /* cudaGetLastError() after the launch was not cudaSuccess */
+    B200W_ERR_WORKSPACE = -8,     /* workspace too small / null */
+    B200W_ERR_BAD_WINDOW = -9     /* SSIM window size must be odd and <= B200W_SSIM_MAX_WINDOW */
+};
+
+#define B200W_SSIM_MAX_WINDOW 11
+
+int b200w_abi_version(void);
+const char* b200w_status_string(int status);
+/* last cudaError_t seen by a failing launch on this thread (0 = none); for diagnostics only */
+int b200w_last_cuda_error(void);
+
+/* floor((n+l-1)/2), or ceil(n/2) for periodization; negative status for a bad mode */
+int b200w_dwt_coeff_len(int n, int l, int mode);
+/* length produced by one synthesis level from m coefficients: 2m-l+2, or 2m for periodization */
+int b200w_idwt_len(int m, int l, int mode);
+
+/*
+ * One analysis level: x (planes,H,W) -> low (planes,Ho,Wo), highs (planes,3,Ho,Wo) with
+ * Ho = b200w_dwt_coeff_len(H,Lh,mode), Wo = b200w_dwt_coeff_len(W,Lw,mode);
+ * band order LH,HL,HH = (W-lo,H-hi),(W-hi,H-lo),(W-hi,H-hi)  (pw/dwt/lowlevel.py:343-347).
+ */
+int b200w_afb2d_f32(const float* x, int64_t x_plane_stride, int64_t x_row_stride,
+                    int planes, int H, int W,
+                    const float* w_lo, const float* w_hi, int Lw,
+                    const float* h_lo, const float* h_hi, int Lh,
+                    int mode, float* low, float* highs, void* stream);
+
+/*
+ * One synthesis level: low (planes,h,w) [strided], highs (planes,3,h,w) dense or NULL (= zeros,
+ * transform2d.py:137-139) -> y (planes,out_h,out_w) dense, where out_h <= b200w_idwt_len(h,Lh,mode)
+ * and out_w <= b200w_idwt_len(w,Lw,mode); a smaller out_h/out_w crops (pw/dwt/lowlevel.py:359-364).
+ */
+int b200w_sfb2d_f32(const float* low, int64_t low_plane_stride, int64_t low_row_stride,
+                    const float* highs, int planes, int h, int w,
+                    const float* w_lo, const float* w_hi, int Lw,
+                    const float* h_lo, const float* h_hi, int Lh,
+                    int mode, float* y, int out_h, int out_w, void* stream);
+
+/*
+ * SSIM forward.  img1,img2: (N,C,H,W) dense.  win: `ws` HOST floats, the normalised 1-D Gaussian
+ * (ssim.py:7-9); the 2-D window of ssim.py:11-15 is its outer product and is applied separably.
+ * out: DEVICE, 1 float (size_average != 0: mean over everything) or N floats (per-sample means,
+ * ssim.py:34-37).  n_maps selects what is saved for the backward: 0 = nothing, 3 = dS/dmu1,
+ * dS/dE[x^2], dS/dE[x1x2] (gradient w.r.t. img1), 4 = those + dS/dmu2 (both gradients);
+ * maps: DEVICE (n_maps,N,C,H,W) or NULL when n_maps == 0.
+ * workspace: DEVICE scratch of at least b200w_ssim_workspace_bytes() (per-CTA partial sums).
+ */
+size_t b200w_ssim_workspace_bytes(int N, int C, int H, int W);
+int b200w_ssim_fwd_f32(const float* img1, const float* img2, int N, int C, int H, int W,
+                       const float* win, int ws, int size_average,
+                       int n_maps, float* maps, float* out,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * SSIM backward.  grad_out: DEVICE, 1 float (size_average) or N floats.  d1 (and d2 if non-NULL,
+ * which needs n_maps == 4): DEVICE (N,C,H,W).
+ */
+int b200w_ssim_bwd_f32(const float* img1, const float* img2, const float* maps, int n_maps,
+                       const float* grad_out, int N, int C, int H, int W,
+                       const float* win, int ws, int size_average,
+                       float* d1, float* d2, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200WAVE_H_ */

@@ -1,0 +1,55 @@
+"""Shared helpers for the test-suite (oracle access, golden-case loading, error metric)."""
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+# north_star tolerance: 1e-5 relative (fp32), measured as max|a-b| / max|b| per tensor
+RTOL_F32 = 1e-5
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    denom = np.abs(b).max()
+    if denom == 0:
+        return np.abs(a).max()
+    return np.abs(a - b).max() / denom
+
+
+def load_dwt_cases():
+    z = np.load(os.path.join(GOLDEN, "dwt_cases.npz"))
+    n = int(z["ncases"])
+    cases = []
+    for i in range(n):
+        pre = "c%02d/" % i
+        case = {k[len(pre):]: z[k] for k in z.files if k.startswith(pre)}
+        case["J"] = int(case["J"])
+        case["mode"] = str(case["mode"])
+        case["wave"] = str(case["wave"])
+        case["id"] = "%02d-%s-J%d-%s-%dx%d" % (i, case["wave"], case["J"], case["mode"],
+                                               case["x"].shape[-2], case["x"].shape[-1])
+        cases.append(case)
+    return cases
+
+
+def load_ssim_cases():
+    z = np.load(os.path.join(GOLDEN, "ssim_cases.npz"))
+    n = int(z["ncases"])
+    cases = []
+    for i in range(n):
+        pre = "s%02d/" % i
+        case = {k[len(pre):]: z[k] for k in z.files if k.startswith(pre)}
+        case["size_average"] = bool(case["size_average"])
+        case["id"] = "%02d-sa%d" % (i, case["size_average"])
+        cases.append(case)
+    return cases
+
+
+def case_filters(case):
+    """(h_col, h_row, g_col, g_row) pairs of prepped taps as the reference's buffers hold them."""
+    return ((case["h0_col"], case["h1_col"]), (case["h0_row"], case["h1_row"]),
+            (case["g0_col"], case["g1_col"]), (case["g0_row"], case["g1_row"]))

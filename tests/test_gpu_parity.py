@@ -1,0 +1,327 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the public modules /
+torch.ops.b200wave (which bind the C ABI), against
+  * the committed golden vectors produced by the unmodified reference, and
+  * the numpy oracle on seeded inputs,
+within the north_star tolerance 1e-5 relative (max|a-b| / max|b| per tensor, fp32), plus
+size-independent properties at BASELINE.json's full sizes."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import b200wave
+from b200wave import lowlevel
+from oracle import dwt_oracle, ssim_oracle
+from helpers import RTOL_F32, case_filters, load_dwt_cases, load_ssim_cases, rel_err
+
+pytestmark = pytest.mark.gpu
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "pywt_standin"))
+
+DWT_CASES = load_dwt_cases()
+SSIM_CASES = load_ssim_cases()
+DEV = "cuda"
+
+
+def cu(a, grad=False):
+    return torch.tensor(np.asarray(a), dtype=torch.float32, device=DEV, requires_grad=grad)
+
+
+def modules_for(case):
+    hc, hr, gc, gr = case_filters(case)
+    # buffers hold reversed analysis taps; the constructor wants them un-reversed (it reverses)
+    xfm = b200wave.DWTForward(J=case["J"], wave=(hc[0][::-1], hc[1][::-1], hr[0][::-1], hr[1][::-1]),
+                              mode=case["mode"]).to(DEV)
+    ifm = b200wave.DWTInverse(wave=(gc[0], gc[1], gr[0], gr[1]), mode=case["mode"]).to(DEV)
+    return xfm, ifm
+
+
+@pytest.mark.parametrize("case", DWT_CASES, ids=[c["id"] for c in DWT_CASES])
+def test_golden_dwt_forward_backward(case):
+    xfm, ifm = modules_for(case)
+    J = case["J"]
+    x = cu(case["x"], grad=True)
+    yl, yh = xfm(x)
+    assert yl.is_contiguous() and all(h.is_contiguous() for h in yh)       # tests/test_dwt.py:47-50
+    assert rel_err(yl.detach().cpu(), case["yl"]) < RTOL_F32
+    for j in range(J):
+        assert tuple(yh[j].shape) == case["yh%d" % j].shape
+        assert rel_err(yh[j].detach().cpu(), case["yh%d" % j]) < RTOL_F32
+    (dx,) = torch.autograd.grad([yl] + list(yh), x, [cu(case["gyl"])] + [cu(case["gyh%d" % j]) for j in range(J)])
+    assert rel_err(dx.cpu(), case["dx"]) < RTOL_F32
+
+
+@pytest.mark.parametrize("case", DWT_CASES, ids=[c["id"] for c in DWT_CASES])
+def test_golden_idwt_forward_backward(case):
+    xfm, ifm = modules_for(case)
+    J = case["J"]
+    cl = cu(case["yl"], grad=True)
+    ch = [cu(case["yh%d" % j], grad=True) for j in range(J)]
+    rec = ifm((cl, ch))
+    assert rec.is_contiguous()
+    assert rel_err(rec.detach().cpu(), case["recon"]) < RTOL_F32
+    grads = torch.autograd.grad(rec, [cl] + ch, cu(case["grec"]))
+    assert rel_err(grads[0].cpu(), case["dcl"]) < RTOL_F32
+    for j in range(J):
+        assert rel_err(grads[1 + j].cpu(), case["dch%d" % j]) < RTOL_F32
+
+
+def _wave_taps(name):
+    import pywt  # the stand-in (test infrastructure)
+    w = pywt.Wavelet(name)
+    return w
+
+
+@pytest.mark.parametrize("wave,J,mode,shape", [
+    ("haar", 3, "zero", (8, 1, 304, 304)),            # BASELINE cfg1
+    ("db3", 3, "symmetric", (4, 1, 304, 304)),        # BASELINE cfg2 shape, smaller batch for the oracle
+    ("db2", 3, "periodization", (3, 2, 127, 100)),
+    ("db4", 2, "reflect", (2, 3, 99, 100)),
+    ("db5", 2, "periodic", (2, 2, 65, 130)),
+    ("db8", 2, "symmetric", (2, 1, 200, 333)),
+    ("db6", 1, "zero", (1, 1, 31, 257)),
+    ("db7", 1, "periodization", (1, 2, 64, 65)),
+    ("bior2.4", 2, "periodization", (2, 2, 64, 64)),
+    ("db1", 1, "reflect", (5, 1, 256, 256)),          # model.py:140 (haar/J=1/reflect on 256x256)
+    ("db10", 1, "symmetric", (1, 1, 70, 90)),         # 20 taps: direct kernel
+])
+def test_oracle_dwt_roundtrip_seeded(wave, J, mode, shape):
+    rng = np.random.default_rng(hash((wave, J, mode)) % (2 ** 32))
+    x = rng.standard_normal(shape).astype(np.float32)
+    xfm = b200wave.DWTForward(J=J, wave=wave, mode=mode).to(DEV)
+    ifm = b200wave.DWTInverse(wave=wave, mode=mode).to(DEV)
+    hc = (xfm.h0_col.flatten().cpu().numpy().astype(np.float64), xfm.h1_col.flatten().cpu().numpy().astype(np.float64))
+    gc = (ifm.g0_col.flatten().cpu().numpy().astype(np.float64), ifm.g1_col.flatten().cpu().numpy().astype(np.float64))
+    tx = cu(x, grad=True)
+    yl, yh = xfm(tx)
+    oyl, oyh = dwt_oracle.dwt_forward(x.astype(np.float64), J, hc, hc, mode)
+    assert rel_err(yl.detach().cpu(), oyl) < RTOL_F32
+    for a, b in zip(yh, oyh):
+        assert rel_err(a.detach().cpu(), b) < RTOL_F32
+    rec = ifm((yl, yh))
+    orec = dwt_oracle.dwt_inverse(oyl, oyh, gc, gc, mode)
+    assert rel_err(rec.detach().cpu(), orec) < RTOL_F32
+    # full chain backward == oracle restatement of the reference's custom backwards
+    g = rng.standard_normal(orec.shape).astype(np.float32)
+    rec.backward(cu(g))
+    # oracle: SFB2D.backward chain (finest first), then AFB2D.backward chain (coarsest first)
+    dy = g.astype(np.float64)
+    dhs = []
+    in_shapes = [x.shape[-2:]] + [h.shape[-2:] for h in oyh[:-1]]
+    for j in range(J):
+        dlow, dhigh = dwt_oracle.sfb2d_backward(dy, gc[0], gc[1], gc[0], gc[1], mode)
+        dhs.append(dhigh)
+        if j + 1 < J:
+            tgt = oyh[j + 1].shape[-2:]
+            L = len(gc[0])
+            full = tuple(2 * m if mode == "periodization" else 2 * m - L + 2 for m in tgt)
+            pad = np.zeros(dlow.shape[:2] + full)
+            pad[..., :dlow.shape[-2], :dlow.shape[-1]] = dlow
+            dy = pad
+    d = dlow
+    for j in reversed(range(J)):
+        d = dwt_oracle.afb2d_backward(d, dhs[j], hc[0], hc[1], hc[0], hc[1], mode, in_shapes[j])
+    assert rel_err(tx.grad.cpu(), d) < RTOL_F32
+    # perfect reconstruction (tests/test_dwt.py:64) where the sizes allow it
+    if all(s % (2 ** J) == 0 for s in shape[-2:]) or mode != "periodization":
+        r = rec.detach().cpu().numpy()[..., :shape[-2], :shape[-1]]
+        assert np.abs(r - x).max() < 2e-4 * max(1.0, np.abs(x).max())
+
+
+def test_full_size_properties_cfg2():
+    """BASELINE cfg2 at full size (64x1x304x304, db3, symmetric, J=3): perfect reconstruction, linearity,
+    contiguity -- size-independent properties instead of an oracle run."""
+    torch.manual_seed(0)
+    x = torch.rand(64, 1, 304, 304, device=DEV)
+    z = torch.rand(64, 1, 304, 304, device=DEV)
+    xfm = b200wave.DWTForward(J=3, wave="db3", mode="symmetric").to(DEV)
+    ifm = b200wave.DWTInverse(wave="db3", mode="symmetric").to(DEV)
+    yl, yh = xfm(x)
+    assert [tuple(h.shape) for h in yh] == [(64, 1, 3, 154, 154), (64, 1, 3, 79, 79), (64, 1, 3, 42, 42)]
+    assert tuple(yl.shape) == (64, 1, 42, 42)
+    rec = ifm((yl, yh))
+    assert tuple(rec.shape) == (64, 1, 304, 304)
+    assert (rec - x).abs().max().item() < 1e-5
+    zl, zh = xfm(z)
+    sl, sh = xfm(2.0 * x - 3.0 * z)
+    assert (sl - (2.0 * yl - 3.0 * zl)).abs().max().item() < 1e-4
+    for a, b, c in zip(sh, yh, zh):
+        assert (a - (2.0 * b - 3.0 * c)).abs().max().item() < 1e-4
+    # every plane is independent: a batch slice transforms to the slice of the transform
+    yl8, yh8 = xfm(x[8:16])
+    assert torch.equal(yl8, yl[8:16]) and all(torch.equal(a, b[8:16]) for a, b in zip(yh8, yh))
+
+
+def test_commutativity_of_subbands():
+    """tests/test_dwt.py:163-197: reconstructing from one sub-band at a time and summing == reconstructing all."""
+    torch.manual_seed(1)
+    x = torch.randn(5, 4, 64, 64, device=DEV)
+    for wave, J, mode in [("db3", 2, "symmetric"), ("db2", 3, "periodization"), ("db4", 2, "zero")]:
+        xfm = b200wave.DWTForward(J=J, wave=wave, mode=mode).to(DEV)
+        ifm = b200wave.DWTInverse(wave=wave, mode=mode).to(DEV)
+        yl, yh = xfm(x)
+        full = ifm((yl, yh))
+        parts = ifm((yl, [None] * J))
+        for j in range(J):
+            for b in range(3):
+                only = [None] * J
+                t = torch.zeros_like(yh[j])
+                t[:, :, b] = yh[j][:, :, b]
+                only[j] = t
+                parts = parts + ifm((torch.zeros_like(yl), only))
+        assert (parts - full).abs().max().item() < 1e-4
+
+
+def test_gradients_match_time_reversed_filters():
+    """tests/test_dwt.py:200-299: AFB2D backward == DWTInverse with (dec_lo[::-1], dec_hi[::-1]); SFB2D backward
+    == DWTForward with those filters -- for modes where the reference's backward is the true adjoint."""
+    torch.manual_seed(2)
+    w = b200wave.Wavelet("db3")
+    for mode in ("zero", "periodization"):
+        xfm = b200wave.DWTForward(J=1, wave="db3", mode=mode).to(DEV)
+        ifm_t = b200wave.DWTInverse(wave=(w.dec_lo[::-1], w.dec_hi[::-1]), mode=mode).to(DEV)
+        x = torch.randn(5, 6, 128, 128, device=DEV, requires_grad=True)
+        yl, yh = xfm(x)
+        gl, gh = torch.randn_like(yl), torch.randn_like(yh[0])
+        (dx,) = torch.autograd.grad([yl, yh[0]], x, [gl, gh])
+        ref = ifm_t((gl, [gh]))
+        assert (dx - ref[..., :128, :128]).abs().max().item() < 1e-4
+
+
+def test_mixed_and_odd_length_filters_direct_kernel():
+    """4-tuple wave with different lengths per axis and an odd-length filter exercise the direct kernels."""
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((2, 2, 40, 52)).astype(np.float32)
+    h_w = (rng.standard_normal(5), rng.standard_normal(5))     # odd length, along W ("col" slot)
+    h_h = (rng.standard_normal(4), rng.standard_normal(4))
+    for mode in ("zero", "symmetric", "periodic", "reflect"):
+        xfm = b200wave.DWTForward(J=1, wave=(h_w[0], h_w[1], h_h[0], h_h[1]), mode=mode).to(DEV)
+        ifm = b200wave.DWTInverse(wave=(h_w[0], h_w[1], h_h[0], h_h[1]), mode=mode).to(DEV)
+        yl, yh = xfm(cu(x))
+        f = lambda t: t.flatten().cpu().numpy().astype(np.float64)
+        oyl, oyh = dwt_oracle.dwt_forward(x.astype(np.float64), 1, (f(xfm.h0_col), f(xfm.h1_col)),
+                                          (f(xfm.h0_row), f(xfm.h1_row)), mode)
+        assert rel_err(yl.cpu(), oyl) < RTOL_F32 and rel_err(yh[0].cpu(), oyh[0]) < RTOL_F32
+        rec = ifm((yl, yh))
+        orec = dwt_oracle.dwt_inverse(oyl, oyh, (f(ifm.g0_col), f(ifm.g1_col)), (f(ifm.g0_row), f(ifm.g1_row)), mode)
+        assert rel_err(rec.cpu(), orec) < RTOL_F32
+
+
+def test_strided_and_noncontiguous_inputs():
+    torch.manual_seed(3)
+    base = torch.randn(4, 3, 70, 90, device=DEV)
+    xfm = b200wave.DWTForward(J=1, wave="db2", mode="symmetric").to(DEV)
+    views = [base[:, :, 3:67, 5:85], base[:, 1:2], base[::2], base.transpose(2, 3), base[:, :, :, ::2]]
+    for v in views:
+        a_l, a_h = xfm(v)
+        b_l, b_h = xfm(v.contiguous())
+        assert torch.equal(a_l, b_l) and torch.equal(a_h[0], b_h[0])
+
+
+def test_error_behaviour_on_gpu():
+    x = torch.zeros(1, 1, 16, 16, device=DEV)
+    for bad in ("constant", "replicate"):            # accepted by mode_to_int, rejected downstream
+        with pytest.raises(ValueError, match="Unkown pad type: %s" % bad):
+            b200wave.DWTForward(mode=bad).to(DEV)(x)
+    with pytest.raises(RuntimeError, match="expected scalar type Float"):
+        b200wave.DWTForward().to(DEV)(x.double())
+    with pytest.raises(IndexError):
+        b200wave.DWTForward().to(DEV)(x[0])
+    with pytest.raises(RuntimeError, match="reflect"):
+        b200wave.DWTForward(wave="db4", mode="reflect").to(DEV)(torch.zeros(1, 1, 4, 4, device=DEV))
+    # empty batch
+    yl, yh = b200wave.DWTForward(J=2, wave="db2").to(DEV)(torch.zeros(0, 3, 16, 16, device=DEV))
+    assert yl.shape == (0, 3, 6, 6) and yh[0].shape == (0, 3, 3, 9, 9)
+
+
+def test_functional_afb2d_sfb2d():
+    torch.manual_seed(4)
+    x = torch.randn(2, 3, 32, 48, device=DEV)
+    w = b200wave.Wavelet("db2")
+    y = lowlevel.afb2d(x, (w.dec_lo, w.dec_hi), mode="periodization")
+    assert y.shape == (2, 12, 16, 24)
+    y5 = y.reshape(2, 3, 4, 16, 24)
+    rec = lowlevel.sfb2d(y5[:, :, 0].contiguous(), y5[:, :, 1], y5[:, :, 2], y5[:, :, 3], (w.rec_lo, w.rec_hi),
+                         mode="periodization")
+    assert (rec - x).abs().max().item() < 1e-5
+
+
+# ------------------------------------------------------------------------------------------- SSIM
+@pytest.mark.parametrize("case", SSIM_CASES, ids=[c["id"] for c in SSIM_CASES])
+def test_golden_ssim(case):
+    a, b = cu(case["img1"], grad=True), cu(case["img2"], grad=True)
+    mod = b200wave.SSIM(window_size=11, size_average=case["size_average"])
+    val = mod(a, b)
+    assert rel_err(np.atleast_1d(val.detach().cpu().numpy()), np.atleast_1d(case["val"])) < RTOL_F32
+    val.backward(cu(case["gout"]) if not case["size_average"] else None)
+    scale = np.abs(case["d1"]).max()
+    if scale > 1e-12:
+        assert rel_err(a.grad.cpu(), case["d1"]) < RTOL_F32
+        assert rel_err(b.grad.cpu(), case["d2"]) < RTOL_F32
+    else:   # ssim(x, x): zero gradient up to fp32 rounding of O(1/NCHW) terms
+        assert a.grad.abs().max().item() < 1e-9
+
+
+@pytest.mark.parametrize("shape,size_average", [
+    ((2, 1, 400, 400), True),        # BASELINE cfg3 shape, small batch for the oracle
+    ((3, 2, 67, 131), False),        # odd sizes: scalar staging path, partial strips
+    ((1, 3, 31, 64), True),
+    ((2, 1, 304, 304), True),        # cfg1
+    ((1, 1, 9, 7), True),            # smaller than the window
+])
+def test_oracle_ssim_seeded(shape, size_average):
+    rng = np.random.default_rng(abs(hash(shape)) % (2 ** 32))
+    x = rng.random(shape).astype(np.float32)
+    y = np.clip(x + 0.1 * rng.standard_normal(shape), 0, 1).astype(np.float32)
+    a, b = cu(x, grad=True), cu(y, grad=True)
+    val = b200wave.ssim(a, b, window_size=11, size_average=size_average)
+    oval = ssim_oracle.ssim(x.astype(np.float64), y.astype(np.float64), 11, size_average)
+    assert rel_err(np.atleast_1d(val.detach().cpu().numpy()), np.atleast_1d(oval)) < RTOL_F32
+    gout = np.linspace(0.5, 1.5, shape[0]) if not size_average else 1.0
+    val.backward(cu(gout) if not size_average else None)
+    o1, o2 = ssim_oracle.ssim_backward(x.astype(np.float64), y.astype(np.float64), gout, 11, size_average)
+    assert rel_err(a.grad.cpu(), o1) < RTOL_F32
+    assert rel_err(b.grad.cpu(), o2) < RTOL_F32
+
+
+def test_ssim_grad_only_second_argument_and_identity():
+    rng = np.random.default_rng(5)
+    x = rng.random((2, 2, 40, 56)).astype(np.float32)
+    y = rng.random((2, 2, 40, 56)).astype(np.float32)
+    a, b = cu(x), cu(y, grad=True)
+    val = b200wave.ssim(a, b)
+    val.backward()
+    _, o2 = ssim_oracle.ssim_backward(x.astype(np.float64), y.astype(np.float64))
+    assert rel_err(b.grad.cpu(), o2) < RTOL_F32 and a.grad is None
+    with torch.no_grad():
+        assert abs(b200wave.ssim(a, a).item() - 1.0) < 1e-6
+    # smaller odd windows go through the same kernel with zero outer taps
+    v5 = b200wave.ssim(a, b.detach(), window_size=5).item()
+    assert abs(v5 - ssim_oracle.ssim(x.astype(np.float64), y.astype(np.float64), 5)) < 1e-6
+
+
+def test_full_size_properties_cfg3():
+    """BASELINE cfg3 at full size (256x1x400x400): symmetry, identity, per-sample means average to the global mean,
+    batch independence."""
+    torch.manual_seed(0)
+    x = torch.rand(256, 1, 400, 400, device=DEV)
+    y = (x + 0.1 * torch.randn_like(x)).clamp_(0, 1)
+    s_xy = b200wave.ssim(x, y)
+    s_yx = b200wave.ssim(y, x)
+    assert abs(s_xy.item() - s_yx.item()) < 1e-6
+    assert abs(b200wave.ssim(x, x).item() - 1.0) < 1e-6
+    per = b200wave.ssim(x, y, size_average=False)
+    assert per.shape == (256,) and abs(per.double().mean().item() - s_xy.item()) < 1e-6
+    per8 = b200wave.ssim(x[8:16], y[8:16], size_average=False)
+    assert torch.allclose(per8, per[8:16], atol=1e-6)
+    xg = x.clone().requires_grad_(True)
+    b200wave.SSIM()(xg, y).backward()
+    assert xg.grad.shape == x.shape and torch.isfinite(xg.grad).all()
+    # the mean's gradient is O(1/NCHW); directional derivative check against a finite difference
+    d = torch.randn_like(x)
+    eps = 1e-2
+    fd = (b200wave.ssim(x + eps * d, y).double() - b200wave.ssim(x - eps * d, y).double()) / (2 * eps)
+    an = (xg.grad.double() * d.double()).sum()
+    assert abs(fd.item() - an.item()) < 2e-3 * max(1e-3, abs(an.item())) + 1e-6

@@ -1,0 +1,89 @@
+"""CPU: the numpy oracle against the golden vectors produced by the unmodified reference
+(tests/golden/make_golden.py).  This is what pins the oracle."""
+import numpy as np
+import pytest
+
+from oracle import dwt_oracle, ssim_oracle
+from helpers import load_dwt_cases, load_ssim_cases, case_filters, rel_err
+
+DWT_CASES = load_dwt_cases()
+SSIM_CASES = load_ssim_cases()
+
+
+@pytest.mark.parametrize("case", DWT_CASES, ids=[c["id"] for c in DWT_CASES])
+def test_dwt_forward_inverse(case):
+    h_col, h_row, g_col, g_row = case_filters(case)
+    J, mode = case["J"], case["mode"]
+    yl, yh = dwt_oracle.dwt_forward(case["x"], J, h_col, h_row, mode)
+    assert rel_err(yl, case["yl"]) < 1e-12
+    for j in range(J):
+        assert yh[j].shape == case["yh%d" % j].shape
+        assert rel_err(yh[j], case["yh%d" % j]) < 1e-12
+    rec = dwt_oracle.dwt_inverse(case["yl"], [case["yh%d" % j] for j in range(J)], g_col, g_row, mode)
+    assert rel_err(rec, case["recon"]) < 1e-12
+
+
+@pytest.mark.parametrize("case", DWT_CASES, ids=[c["id"] for c in DWT_CASES])
+def test_dwt_backward_chains(case):
+    """AFB2D.backward / SFB2D.backward restatements chained over J levels == reference autograd."""
+    h_col, h_row, g_col, g_row = case_filters(case)
+    J, mode = case["J"], case["mode"]
+    # forward input sizes per level
+    shapes = [case["x"].shape[-2:]]
+    for j in range(J - 1):
+        shapes.append(case["yh%d" % j].shape[-2:])
+    # d(yl, yh)/dx : coarsest level first
+    d = case["gyl"]
+    for j in reversed(range(J)):
+        d = dwt_oracle.afb2d_backward(d, case["gyh%d" % j], h_col[0], h_col[1], h_row[0], h_row[1], mode, shapes[j])
+    assert rel_err(d, case["dx"]) < 1e-12
+    # d recon / d(yl, yh): finest level first; the 'unpad' crop back-propagates as zero padding
+    dy = case["grec"]
+    for j in range(J):
+        dlow, dhigh = dwt_oracle.sfb2d_backward(dy, g_col[0], g_col[1], g_row[0], g_row[1], mode)
+        assert rel_err(dhigh, case["dch%d" % j]) < 1e-12
+        if j + 1 < J:
+            tgt = case["yh%d" % (j + 1)].shape[-2:]   # size of the ll that level j+1 reconstructed
+            full = (dwt_oracle_len(tgt[0], len(g_row[0]), mode), dwt_oracle_len(tgt[1], len(g_col[0]), mode))
+            pad = np.zeros(dlow.shape[:2] + full, dtype=dlow.dtype)
+            pad[..., :dlow.shape[-2], :dlow.shape[-1]] = dlow
+            dy = pad
+        else:
+            assert rel_err(dlow, case["dcl"]) < 1e-12
+
+
+def dwt_oracle_len(m, L, mode):
+    return 2 * m if mode in ("per", "periodization") else 2 * m - L + 2
+
+
+@pytest.mark.parametrize("case", SSIM_CASES, ids=[c["id"] for c in SSIM_CASES])
+def test_ssim_value_and_grads(case):
+    val = ssim_oracle.ssim(case["img1"], case["img2"], 11, case["size_average"])
+    assert rel_err(np.atleast_1d(val), np.atleast_1d(case["val"])) < 1e-12
+    d1, d2 = ssim_oracle.ssim_backward(case["img1"], case["img2"], case["gout"], 11, case["size_average"])
+    if np.abs(case["d1"]).max() > 1e-12:
+        assert rel_err(d1, case["d1"]) < 1e-10
+        assert rel_err(d2, case["d2"]) < 1e-10
+    else:  # ssim(x, x): gradient is zero up to rounding
+        assert np.abs(d1).max() < 1e-12
+
+
+def test_known_answers():
+    # docs/dwt.rst:64-75: db3, zero, J=3 on 64x64 -> yl 12x12, yh 34, 19, 12
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "pywt_standin"))
+    import pywt
+    w = pywt.Wavelet("db3")
+    h = dwt_oracle.prep_afb(w.dec_lo, w.dec_hi)
+    x = np.random.default_rng(0).standard_normal((1, 1, 64, 64))
+    yl, yh = dwt_oracle.dwt_forward(x, 3, h, h, "zero")
+    assert yl.shape[-2:] == (12, 12)
+    assert [t.shape[-1] for t in yh] == [34, 19, 12]
+    # haar on a constant image: LL = 2c, details 0
+    w = pywt.Wavelet("haar")
+    h = dwt_oracle.prep_afb(w.dec_lo, w.dec_hi)
+    yl, yh = dwt_oracle.dwt_forward(np.full((1, 1, 8, 8), 3.0), 1, h, h, "zero")
+    assert np.allclose(yl, 6.0) and np.allclose(yh[0], 0.0)
+    # ssim(x, x) == 1
+    a = np.random.default_rng(1).random((1, 2, 20, 20))
+    assert abs(ssim_oracle.ssim(a, a) - 1.0) < 1e-12
