@@ -163,15 +163,23 @@ def test_commutativity_of_subbands():
         ifm = b200wave.DWTInverse(wave=wave, mode=mode).to(DEV)
         yl, yh = xfm(x)
         full = ifm((yl, yh))
-        parts = ifm((yl, [None] * J))
+        zeros = [torch.zeros_like(h) for h in yh]
+        parts = ifm((yl, zeros))
         for j in range(J):
             for b in range(3):
-                only = [None] * J
+                only = list(zeros)
                 t = torch.zeros_like(yh[j])
                 t[:, :, b] = yh[j][:, :, b]
                 only[j] = t
                 parts = parts + ifm((torch.zeros_like(yl), only))
         assert (parts - full).abs().max().item() < 1e-4
+        # None == zeros for the detail bands (pw/dwt/transform2d.py:137-139); single level so no 'unpad' is skipped
+        if J == 1:
+            assert torch.equal(ifm((yl, [None])), ifm((yl, zeros)))
+    xfm = b200wave.DWTForward(J=1, wave="db3", mode="zero").to(DEV)
+    ifm = b200wave.DWTInverse(wave="db3", mode="zero").to(DEV)
+    yl, yh = xfm(x)
+    assert torch.allclose(ifm((yl, [None])), ifm((yl, [torch.zeros_like(yh[0])])), atol=1e-6)
 
 
 def test_gradients_match_time_reversed_filters():
