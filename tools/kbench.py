@@ -1,0 +1,91 @@
+"""Kernel micro-benchmark: per-launch duration of single levels / SSIM kernels (CUDA graph of back-to-back
+launches over rotating inputs larger than L2, CUDA events).
+
+    python tools/kbench.py [dwt|ssim|all]
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+import b200wave  # noqa: E402
+from b200wave import lowlevel, ops  # noqa: E402
+from b200wave.ssim import _win_taps  # noqa: E402
+
+PEAK = 6538.9
+dev = "cuda"
+
+
+def timeit(fn, nsets, reps=60):
+    for i in range(3):
+        fn(i)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    keep = []
+    with torch.cuda.graph(g):
+        for i in range(reps):
+            keep.append(fn(i))
+            if len(keep) > nsets:
+                keep.pop(0)
+    g.replay()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    g.replay()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps * 1e-3
+
+
+def dwt_case(n, h, w, wave, mode):
+    xfm = b200wave.DWTForward(J=1, wave=wave, mode=mode).to(dev)
+    ifm = b200wave.DWTInverse(wave=wave, mode=mode).to(dev)
+    m = lowlevel.mode_to_int(mode)
+    nbytes_in = 4 * n * h * w
+    nsets = max(2, int(2 * 126e6 * 1.05 / nbytes_in) + 1)
+    xs = [torch.rand(n, 1, h, w, device=dev) for _ in range(nsets)]
+    with torch.no_grad():
+        cs = [xfm(x) for x in xs]
+        ho, wo = cs[0][0].shape[-2:]
+        by = 4 * n * (h * w + 4 * ho * wo)
+        ta = timeit(lambda i: lowlevel.AFB2D.apply(xs[i % nsets], xfm.h0_col, xfm.h1_col, xfm.h0_row, xfm.h1_row, m), nsets)
+        ts = timeit(lambda i: lowlevel.SFB2D.apply(cs[i % nsets][0], cs[i % nsets][1][0], ifm.g0_col, ifm.g1_col,
+                                                   ifm.g0_row, ifm.g1_row, m), nsets)
+    print("dwt %-5s %-13s %4dx%4dx%4d  afb %7.1f us %6.0f GB/s (%4.1f%%)   sfb %7.1f us %6.0f GB/s (%4.1f%%)" % (
+        wave, mode, n, h, w, ta * 1e6, by / ta / 1e9, by / ta / 1e9 / PEAK * 100, ts * 1e6, by / ts / 1e9,
+        by / ts / 1e9 / PEAK * 100), flush=True)
+
+
+def ssim_case(n, h, w):
+    nsets = max(2, int(2 * 126e6 / (8 * n * h * w)) + 1)
+    a = [torch.rand(n, 1, h, w, device=dev) for _ in range(nsets)]
+    b = [(t + 0.1 * torch.randn_like(t)).clamp_(0, 1) for t in a]
+    win = _win_taps(11)
+    g = torch.ones((), device=dev)
+    with torch.no_grad():
+        t0 = timeit(lambda i: ops.ssim_fwd(a[i % nsets], b[i % nsets], win, True, 0), nsets, 20)
+        t3 = timeit(lambda i: ops.ssim_fwd(a[i % nsets], b[i % nsets], win, True, 3), nsets, 20)
+        maps = [ops.ssim_fwd(a[i], b[i], win, True, 3)[1] for i in range(nsets)]
+        tb = timeit(lambda i: ops.ssim_bwd(a[i % nsets], b[i % nsets], maps[i % nsets], g, win, True, False), nsets, 20)
+    px = n * h * w
+    print("ssim %4dx%4dx%4d  fwd(no maps) %7.1f us %6.1f Gpx/s %5.0f GB/s | fwd+3maps %7.1f us %5.0f GB/s | "
+          "bwd %7.1f us %5.0f GB/s | fwd+bwd algorithmic 20 B/px: %5.0f GB/s (%4.1f%%)" % (
+              n, h, w, t0 * 1e6, px / t0 / 1e9, 8 * px / t0 / 1e9, t3 * 1e6, 20 * px / t3 / 1e9, tb * 1e6,
+              24 * px / tb / 1e9, 20 * px / (t3 + tb) / 1e9, 20 * px / (t3 + tb) / 1e9 / PEAK * 100), flush=True)
+
+
+what = sys.argv[1] if len(sys.argv) > 1 else "all"
+if what in ("dwt", "all"):
+    dwt_case(64, 304, 304, "db3", "symmetric")
+    dwt_case(64, 154, 154, "db3", "symmetric")
+    dwt_case(64, 79, 79, "db3", "symmetric")
+    dwt_case(64, 304, 304, "haar", "zero")
+    dwt_case(64, 1024, 1024, "db3", "symmetric")
+    dwt_case(64, 1024, 1024, "haar", "zero")
+    dwt_case(64, 1024, 1024, "db8", "symmetric")
+    dwt_case(16, 2048, 2048, "db4", "zero")
+    dwt_case(64, 1024, 1024, "db2", "periodization")
+if what in ("ssim", "all"):
+    ssim_case(256, 400, 400)
+    ssim_case(64, 1024, 1024)
+    ssim_case(8, 304, 304)
