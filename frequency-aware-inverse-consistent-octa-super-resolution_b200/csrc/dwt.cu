@@ -130,20 +130,21 @@ struct AfbCfg {
 // the padding mode is applied as an index map, "zero" = zero fill.
 template <int V, int ROWS, int PITCH, int NT>
 __device__ __forceinline__ void stage_analysis(unsigned patch_s, const float* __restrict__ xp, long long rs, int r0,
-                                               int c0, int H, int W, int mode, int tid) {
+                                               int c0, int H, int W, int mode, int nrows, int ncols, int tid) {
     constexpr int NVC = PITCH / V;   // vector columns per row
     constexpr int NRG = NT / NVC;    // row groups
     if (tid >= NVC * NRG) return;
     const int cv = tid % NVC;
     const int rg = tid / NVC;
+    if (V * cv >= ncols) return;     // columns that feed no valid output of an edge tile are not staged
     const int sc0 = c0 + V * cv;
     const bool col_in = sc0 >= 0 && sc0 + V <= W;
     unsigned dst = patch_s + (unsigned)((rg * PITCH + V * cv) * 4);
-    if (col_in && r0 >= 0 && r0 + ROWS <= H) {
+    if (col_in && r0 >= 0 && r0 + nrows <= H) {
         const float* src = xp + (long long)(r0 + rg) * rs + sc0;
         const long long step = (long long)NRG * rs;
 #pragma unroll 4
-        for (int r = rg; r < ROWS; r += NRG) {
+        for (int r = rg; r < nrows; r += NRG) {
             cp_async<V>(dst, src);
             dst += NRG * PITCH * 4;
             src += step;
@@ -153,7 +154,7 @@ __device__ __forceinline__ void stage_analysis(unsigned patch_s, const float* __
     int ci[V];
 #pragma unroll
     for (int e = 0; e < V; ++e) ci[e] = ext_index(sc0 + e, W, mode);
-    for (int r = rg; r < ROWS; r += NRG, dst += NRG * PITCH * 4) {
+    for (int r = rg; r < nrows; r += NRG, dst += NRG * PITCH * 4) {
         const int sr = ext_index(r0 + r, H, mode);
         if (sr < 0) {
             cp_async_zero<V>(dst, xp);
@@ -175,9 +176,12 @@ __device__ __forceinline__ void afb_issue(unsigned patch_s, const AfbParams& p, 
     const int r0 = 2 * it.th * TH - p.offH;  // source row of patch row 0
     const int c0 = 2 * it.tw * TW - p.offW;
     const float* xp = p.x + (long long)it.plane * p.x_ps;
-    if (p.in_vec == 4) stage_analysis<4, Cfg::PR, Cfg::PCP, NT>(patch_s, xp, p.x_rs, r0, c0, p.H, p.W, p.mode, tid);
-    else if (p.in_vec == 2) stage_analysis<2, Cfg::PR, Cfg::PCP, NT>(patch_s, xp, p.x_rs, r0, c0, p.H, p.W, p.mode, tid);
-    else stage_analysis<1, Cfg::PR, Cfg::PCP, NT>(patch_s, xp, p.x_rs, r0, c0, p.H, p.W, p.mode, tid);
+    // an edge tile only needs the rows / columns its valid outputs read: 2*(n_valid-1) + L of them
+    const int nrows = min(Cfg::PR, 2 * (min(TH, p.Ho - it.th * TH) - 1) + L);
+    const int ncols = min(Cfg::PCP, 2 * (min(TW, p.Wo - it.tw * TW) - 1) + L);
+    if (p.in_vec == 4) stage_analysis<4, Cfg::PR, Cfg::PCP, NT>(patch_s, xp, p.x_rs, r0, c0, p.H, p.W, p.mode, nrows, ncols, tid);
+    else if (p.in_vec == 2) stage_analysis<2, Cfg::PR, Cfg::PCP, NT>(patch_s, xp, p.x_rs, r0, c0, p.H, p.W, p.mode, nrows, ncols, tid);
+    else stage_analysis<1, Cfg::PR, Cfg::PCP, NT>(patch_s, xp, p.x_rs, r0, c0, p.H, p.W, p.mode, nrows, ncols, tid);
 }
 
 template <int L, int TW, int TH, int NT>
@@ -359,23 +363,24 @@ struct SfbCfg {
 template <int V, int KH, int KWP, int NT>
 __device__ __forceinline__ void stage_synthesis(unsigned sub_s, const float* __restrict__ lowp, long long low_rs,
                                                 const float* __restrict__ hip, size_t band, int kH0, int kW0, int h,
-                                                int w, bool periodic, int tid) {
+                                                int w, bool periodic, int nrows, int ncols, int tid) {
     constexpr int NVC = KWP / V;
     constexpr int NRG = NT / NVC;
     constexpr unsigned PBB = KH * KWP * 4;  // bytes of one band's patch
     if (tid >= NVC * NRG) return;
     const int cv = tid % NVC;
     const int rg = tid / NVC;
+    if (V * cv >= ncols) return;
     const int kc0 = kW0 + V * cv;
     const bool col_in = kc0 >= 0 && kc0 + V <= w;
     unsigned dst = sub_s + (unsigned)((rg * KWP + V * cv) * 4);
-    if (col_in && kH0 >= 0 && kH0 + KH <= h && hip != nullptr) {
+    if (col_in && kH0 >= 0 && kH0 + nrows <= h && hip != nullptr) {
         const float* lp = lowp + (long long)(kH0 + rg) * low_rs + kc0;
         const float* hp = hip + (size_t)(kH0 + rg) * w + kc0;
         const long long lstep = (long long)NRG * low_rs;
         const size_t hstep = (size_t)NRG * w;
 #pragma unroll 2
-        for (int r = rg; r < KH; r += NRG) {
+        for (int r = rg; r < nrows; r += NRG) {
             cp_async<V>(dst, lp);
             cp_async<V>(dst + PBB, hp);
             cp_async<V>(dst + 2 * PBB, hp + band);
@@ -389,7 +394,7 @@ __device__ __forceinline__ void stage_synthesis(unsigned sub_s, const float* __r
     int ci[V];
 #pragma unroll
     for (int e = 0; e < V; ++e) ci[e] = coef_index(kc0 + e, w, periodic);
-    for (int r = rg; r < KH; r += NRG, dst += NRG * KWP * 4) {
+    for (int r = rg; r < nrows; r += NRG, dst += NRG * KWP * 4) {
         const int kr = coef_index(kH0 + r, h, periodic);
         if (kr < 0) {
 #pragma unroll
@@ -430,9 +435,14 @@ __device__ __forceinline__ void sfb_issue(unsigned sub_s, const SfbParams& p, co
     const size_t band = (size_t)p.h * p.w;
     const float* lowp = p.low + (long long)it.plane * p.low_ps;
     const float* hip = p.highs ? p.highs + (size_t)it.plane * 3 * band : nullptr;
+    // coefficient rows / columns feeding the valid outputs of an edge tile: local a <= a_max -> k_local <= a_max/2 + H2-1
+    const int amax_h = min(TH - 1, p.offH + p.out_h - 1 - (p.a0H + it.th * TH));
+    const int amax_w = min(TW - 1, p.offW + p.out_w - 1 - (p.a0W + it.tw * TW));
+    const int nrows = min(Cfg::KH, amax_h / 2 + Cfg::H2);
+    const int ncols = min(Cfg::KWP, amax_w / 2 + Cfg::H2);
     // kW0 is even whenever in_vec2 is set (checked on the host)
-    if (p.in_vec2) stage_synthesis<2, Cfg::KH, Cfg::KWP, NT>(sub_s, lowp, p.low_rs, hip, band, kH0, kW0, p.h, p.w, p.periodic, tid);
-    else stage_synthesis<1, Cfg::KH, Cfg::KWP, NT>(sub_s, lowp, p.low_rs, hip, band, kH0, kW0, p.h, p.w, p.periodic, tid);
+    if (p.in_vec2) stage_synthesis<2, Cfg::KH, Cfg::KWP, NT>(sub_s, lowp, p.low_rs, hip, band, kH0, kW0, p.h, p.w, p.periodic, nrows, ncols, tid);
+    else stage_synthesis<1, Cfg::KH, Cfg::KWP, NT>(sub_s, lowp, p.low_rs, hip, band, kH0, kW0, p.h, p.w, p.periodic, nrows, ncols, tid);
 }
 
 template <int L, int TW, int TH, int NT>
@@ -706,7 +716,7 @@ static int launch_afb_tiled(AfbParams& p, cudaStream_t st) {
     // one unless it wastes noticeably more of the padded output area
     const long long a32 = (long long)ceil_div(p.Wo, 32) * 32;
     const long long a64 = (long long)ceil_div(p.Wo, 64) * 64;
-    if (a64 * 100 <= a32 * 103) {
+    if (p.Wo >= 128 && a64 * 100 <= a32 * 103) {
         constexpr int TW = 64, TH = 32, NT = 256;
         static int occ[kMaxDevices] = {0};
         return launch_tiles(afb2d_tile_kernel<L, TW, TH, NT>, p, ceil_div(p.Wo, TW), ceil_div(p.Ho, TH), NT,
