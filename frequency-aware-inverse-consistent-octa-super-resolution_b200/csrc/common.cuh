@@ -68,6 +68,29 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// cp.async (LDGSTS): global -> shared without register staging.  `dst` is a 32-bit shared-window address.
+template <int V>
+__device__ __forceinline__ void cp_async(unsigned dst, const float* src) {
+    if (V == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    else if (V == 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+// src-size 0: nothing is read, the destination is zero-filled (`src` only has to be a valid address)
+template <int V>
+__device__ __forceinline__ void cp_async_zero(unsigned dst, const float* src) {
+    const int z = 0;
+    if (V == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(z) : "memory");
+    else if (V == 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(z) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(z) : "memory");
+}
+__device__ __forceinline__ void cp_async4_if(unsigned dst, const float* src, bool valid) {
+    const int n = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 int set_last_cuda_error(cudaError_t e);
 
 }  // namespace b200w

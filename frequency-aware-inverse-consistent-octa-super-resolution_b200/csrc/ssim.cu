@@ -37,31 +37,30 @@ struct SsimParams {
     int planes, C, H, W;
     int strips, nseg, seg_rows;
     int n_maps, size_average;
+    int vec_ok;           // 16 B staging copies allowed (W % 4 == 0 and every base 16 B aligned)
     float inv_count;      // 1/(N*C*H*W) or 1/(C*H*W)
     float win[kWin];
 };
 
-// stage rows [row0, row0+nrows) x cols [C0-8, C0+72) of `src` plane into dst[nrows][kPW], zero outside
-__device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__ src, int row0, int nrows, int C0,
-                                           int H, int W, bool vec_ok, int tid) {
-    constexpr int CH = kPW / 4;  // 20 chunks of 4 floats per row
-    for (int idx = tid; idx < nrows * CH; idx += kThreads) {
-        const int r = idx / CH, ch = idx - r * CH;
+// Stage rows [row0, row0+nrows) x cols [C0-8, C0+72) of one plane into dst[nrows][kPW] with cp.async, zero
+// outside the image (= the conv's zero padding).  Thread = one vector column, walking down the rows.
+template <int V>
+__device__ __forceinline__ void stage_rows(unsigned dst_s, const float* __restrict__ src, int row0, int nrows, int C0,
+                                           int H, int W, int tid) {
+    constexpr int NVC = kPW / V;
+    constexpr int NRG = kThreads / NVC;
+    if (tid >= NVC * NRG) return;
+    const int cv = tid % NVC;
+    const int rg = tid / NVC;
+    const int gc = C0 - 8 + V * cv;
+    const bool col_in = gc >= 0 && gc + V <= W;   // V == 4 needs W % 4 == 0: a chunk is entirely in or out
+    unsigned dst = dst_s + (unsigned)((rg * kPW + V * cv) * 4);
+    const float* p = src + (long long)(row0 + rg) * W + gc;
+    const long long step = (long long)NRG * W;
+    for (int r = rg; r < nrows; r += NRG, dst += NRG * kPW * 4, p += step) {
         const int gr = row0 + r;
-        const int gc = C0 - 8 + 4 * ch;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gr >= 0 && gr < H) {
-            const float* rowp = src + (long long)gr * W;
-            if (vec_ok) {  // W % 4 == 0 and 16B-aligned base: a chunk is entirely inside or outside
-                if (gc >= 0 && gc < W) v = __ldg(reinterpret_cast<const float4*>(rowp + gc));
-            } else {
-                if (gc >= 0 && gc < W) v.x = __ldg(rowp + gc);
-                if (gc + 1 >= 0 && gc + 1 < W) v.y = __ldg(rowp + gc + 1);
-                if (gc + 2 >= 0 && gc + 2 < W) v.z = __ldg(rowp + gc + 2);
-                if (gc + 3 >= 0 && gc + 3 < W) v.w = __ldg(rowp + gc + 3);
-            }
-        }
-        *reinterpret_cast<float4*>(dst + r * kPW + 4 * ch) = v;
+        if (col_in && gr >= 0 && gr < H) cp_async<V>(dst, p);
+        else cp_async_zero<V>(dst, src);
     }
 }
 
@@ -69,10 +68,11 @@ __device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__
 template <bool FWD, int NC>
 __global__ void __launch_bounds__(kThreads) ssim_stream_kernel(const __grid_constant__ SsimParams p) {
     constexpr int NI = FWD ? 2 : NC;
+    constexpr int SB = NI * kCR * kPW;         // floats per staging buffer
     extern __shared__ __align__(16) float smem[];
-    float* stage = smem;                       // [NI][kCR][kPW]
-    float* hbuf = smem + NI * kCR * kPW;       // [NC][kHR][kTW]
+    float* hbuf = smem + 2 * SB;               // [NC][kHR][kTW]   (two staging buffers [NI][kCR][kPW] first)
     __shared__ float red[kThreads / 32];
+    const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem);
 
     const int tid = threadIdx.x;
     int bid = blockIdx.x;
@@ -86,76 +86,83 @@ __global__ void __launch_bounds__(kThreads) ssim_stream_kernel(const __grid_cons
     const int H = p.H, W = p.W;
 
     const float* src[NI];
-    bool vec_ok = (W % 4) == 0;
 #pragma unroll
-    for (int i = 0; i < NI; ++i) {
-        src[i] = p.in[i] + (long long)plane * p.plane_elems;
-        vec_ok = vec_ok && ((reinterpret_cast<uintptr_t>(src[i]) & 15) == 0);
-    }
+    for (int i = 0; i < NI; ++i) src[i] = p.in[i] + (long long)plane * p.plane_elems;
 
     float g = 0.f;
     if (!FWD) g = __ldg(p.grad_out + (p.size_average ? 0 : plane / p.C)) * p.inv_count;
     float local_sum = 0.f;
 
-    // iteration -1 is the prologue that fills the 10 carried rows [S0-5, S0+5)
+    // chunk q covers horizontally-blurred rows [S0 + 32q + 5, +32); chunk -1 is the prologue [S0-5, S0+5)
     const int niter = (S1 - S0 + kCR - 1) / kCR;
-    for (int q = -1; q < niter; ++q) {
+    auto issue = [&](int q, int buf) {
         const int nrows = q < 0 ? 2 * kHalo : kCR;
-        const int in_row0 = q < 0 ? S0 - kHalo : S0 + kCR * q + kHalo;  // image row of staged row 0
-        const int hrow0 = q < 0 ? 0 : 2 * kHalo;                        // hbuf row receiving staged row 0
+        const int in_row0 = q < 0 ? S0 - kHalo : S0 + kCR * q + kHalo;
 #pragma unroll
-        for (int i = 0; i < NI; ++i) stage_rows(stage + i * kCR * kPW, src[i], in_row0, nrows, C0, H, W, vec_ok, tid);
-        __syncthreads();
+        for (int i = 0; i < NI; ++i) {
+            const unsigned d = smem_s + (unsigned)((buf * SB + i * kCR * kPW) * 4);
+            if (p.vec_ok) stage_rows<4>(d, src[i], in_row0, nrows, C0, H, W, tid);
+            else stage_rows<1>(d, src[i], in_row0, nrows, C0, H, W, tid);
+        }
+    };
+    issue(-1, 0);
+    cp_async_commit();
 
-        // ---- horizontal pass: item = (row, quad of 4 output columns)
-        for (int item = tid; item < nrows * (kTW / 4); item += kThreads) {
-            const int cq = item % (kTW / 4);
-            const int r = item / (kTW / 4);
-            float acc[NC][4];
+    for (int q = -1; q < niter; ++q) {
+        const int buf = (q + 1) & 1;
+        if (q + 1 < niter) issue(q + 1, buf ^ 1);   // prefetch the next chunk while this one is filtered
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const float* stage = smem + buf * SB;
+        const int nrows = q < 0 ? 2 * kHalo : kCR;
+        const int hrow0 = q < 0 ? 0 : 2 * kHalo;   // hbuf row receiving staged row 0
+
+        // ---- horizontal pass: item = (row, quad of 4 output columns); 128-bit shared loads and stores
+        {
+            const int cq = tid % (kTW / 4);
+            int r = tid / (kTW / 4);
+            const float* sp0 = stage + r * kPW + 4 * cq;
+            float* hp = hbuf + (hrow0 + r) * kTW + 4 * cq;
+            constexpr int RSTEP = kThreads / (kTW / 4);
+            for (; r < nrows; r += RSTEP, sp0 += RSTEP * kPW, hp += RSTEP * kTW) {
+                float acc[NC][4];
 #pragma unroll
-            for (int m = 0; m < NC; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
-            float v[NI][20];
+                for (int m = 0; m < NC; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
+                float v[NI][20];
 #pragma unroll
-            for (int i = 0; i < NI; ++i) {
-                const float4* sp = reinterpret_cast<const float4*>(stage + i * kCR * kPW + r * kPW + 4 * cq);
+                for (int i = 0; i < NI; ++i) {
 #pragma unroll
-                for (int c = 0; c < 5; ++c) {
-                    const float4 t = sp[c];
-                    v[i][4 * c] = t.x;
-                    v[i][4 * c + 1] = t.y;
-                    v[i][4 * c + 2] = t.z;
-                    v[i][4 * c + 3] = t.w;
-                }
-            }
-            // output o (0..3) of this quad is image col C0+4cq+o = staged col 4cq+o+8; its window is staged
-            // cols 4cq+o+3 .. 4cq+o+13, i.e. v[o+3+d], d = 0..10
-#pragma unroll
-            for (int i = 3; i < 17; ++i) {
-                float ch[NC];
-                if (FWD) {
-                    const float x1 = v[0][i], x2 = v[1][i];
-                    ch[0] = x1;
-                    ch[1] = x2;
-                    ch[2] = x1 * x1;
-                    ch[3] = x2 * x2;
-                    ch[4] = x1 * x2;
-                } else {
-#pragma unroll
-                    for (int m = 0; m < NC; ++m) ch[m] = v[m][i];
-                }
-#pragma unroll
-                for (int o = 0; o < 4; ++o) {
-                    const int d = i - 3 - o;
-                    if (d >= 0 && d < kWin) {
-#pragma unroll
-                        for (int m = 0; m < NC; ++m) acc[m][o] = fmaf(p.win[d], ch[m], acc[m][o]);
+                    for (int c = 0; c < 5; ++c) {
+                        const float4 t = reinterpret_cast<const float4*>(sp0 + i * kCR * kPW)[c];
+                        v[i][4 * c] = t.x; v[i][4 * c + 1] = t.y; v[i][4 * c + 2] = t.z; v[i][4 * c + 3] = t.w;
                     }
                 }
-            }
+                // output o (0..3) of this quad is image col C0+4cq+o = staged col 4cq+o+8; its window is staged
+                // cols 4cq+o+3 .. 4cq+o+13, i.e. v[o+3+d], d = 0..10
 #pragma unroll
-            for (int m = 0; m < NC; ++m)
-                *reinterpret_cast<float4*>(hbuf + (m * kHR + hrow0 + r) * kTW + 4 * cq) =
-                    make_float4(acc[m][0], acc[m][1], acc[m][2], acc[m][3]);
+                for (int i = 3; i < 17; ++i) {
+                    float ch[NC];
+                    if (FWD) {
+                        const float x1 = v[0][i], x2 = v[1][i];
+                        ch[0] = x1; ch[1] = x2; ch[2] = x1 * x1; ch[3] = x2 * x2; ch[4 % NC] = x1 * x2;
+                    } else {
+#pragma unroll
+                        for (int m = 0; m < NC; ++m) ch[m] = v[m][i];
+                    }
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) {
+                        const int d = i - 3 - o;
+                        if (d >= 0 && d < kWin) {
+#pragma unroll
+                            for (int m = 0; m < NC; ++m) acc[m][o] = fmaf(p.win[d], ch[m], acc[m][o]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int m = 0; m < NC; ++m)
+                    *reinterpret_cast<float4*>(hp + m * kHR * kTW) = make_float4(acc[m][0], acc[m][1], acc[m][2], acc[m][3]);
+            }
         }
         __syncthreads();
         if (q < 0) continue;
@@ -169,11 +176,12 @@ __global__ void __launch_bounds__(kThreads) ssim_stream_kernel(const __grid_cons
             for (int m = 0; m < NC; ++m)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[m][i] = 0.f;
+            const float* hb = hbuf + (8 * s) * kTW + c;
 #pragma unroll
             for (int rr = 0; rr < 8 + kWin - 1; ++rr) {
 #pragma unroll
                 for (int m = 0; m < NC; ++m) {
-                    const float t = hbuf[(m * kHR + 8 * s + rr) * kTW + c];
+                    const float t = hb[(m * kHR + rr) * kTW];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int d = rr - i;
@@ -182,50 +190,64 @@ __global__ void __launch_bounds__(kThreads) ssim_stream_kernel(const __grid_cons
                 }
             }
             const int col = C0 + c;
-            if (col < W) {
+            const int row0 = S0 + kCR * q + 8 * s;
+            if (col < W && row0 < S1) {
+                const long long off = (long long)plane * p.plane_elems + (long long)row0 * W + col;
+                if (FWD) {
+                    float* m0 = p.out0 + off;
+                    const long long ms = p.map_stride;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int row = S0 + kCR * q + 8 * s + i;
-                    if (row < S1) {
-                        const long long off = (long long)plane * p.plane_elems + (long long)row * W + col;
-                        if (FWD) {
+                    for (int i = 0; i < 8; ++i) {
+                        if (row0 + i < S1) {
                             const float C1 = 0.0001f, C2 = 0.0009f;
                             const float mu1 = acc[0][i], mu2 = acc[1][i];
                             const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
-                            const float s11 = acc[2][i] - mu1_sq, s22 = acc[3][i] - mu2_sq, s12 = acc[4][i] - mu12;
+                            const float s11 = acc[2][i] - mu1_sq, s22 = acc[3][i] - mu2_sq, s12 = acc[4 % NC][i] - mu12;
                             const float A1 = 2.f * mu12 + C1, A2 = 2.f * s12 + C2;
                             const float B1 = mu1_sq + mu2_sq + C1, B2 = s11 + s22 + C2;
-                            const float inv = 1.f / (B1 * B2);
+                            const float inv = __fdividef(1.f, B1 * B2);   // B1, B2 >= ~1e-4: one MUFU.RCP, 2 ulp
                             const float S = (A1 * A2) * inv;
                             local_sum += S;
                             if (p.n_maps) {
-                                const float k = 2.f * (A2 - A1) * inv;               // common factor of dS/dmu
-                                const float e = 2.f * S * (1.f / B1 - 1.f / B2);
-                                p.out0[off] = mu2 * k - mu1 * e;                     // M0 = dS/dmu1
-                                p.out0[p.map_stride + off] = -S / B2;                // M1
-                                p.out0[2 * p.map_stride + off] = 2.f * A1 * inv;     // M2
-                                if (p.n_maps == 4) p.out0[3 * p.map_stride + off] = mu1 * k - mu2 * e;  // M3
+                                const float k = 2.f * (A2 - A1) * inv;            // common factor of dS/dmu
+                                const float e = 2.f * S * (B2 - B1) * inv;        // 2 S (1/B1 - 1/B2)
+                                m0[0] = mu2 * k - mu1 * e;                        // M0 = dS/dmu1
+                                m0[ms] = -S * B1 * inv;                           // M1 = -S / B2
+                                m0[2 * ms] = 2.f * A1 * inv;                      // M2
+                                if (p.n_maps == 4) m0[3 * ms] = mu1 * k - mu2 * e;  // M3 = dS/dmu2
                             }
-                        } else {
-                            const float x1 = __ldg(p.img1 + off), x2 = __ldg(p.img2 + off);
-                            p.out0[off] = g * (acc[0][i] + 2.f * x1 * acc[1][i] + x2 * acc[2][i]);
-                            if (NC == 4 && p.out1)
-                                p.out1[off] = g * (acc[NC - 1][i] + 2.f * x2 * acc[1][i] + x1 * acc[2][i]);
                         }
+                        m0 += W;
+                    }
+                } else {
+                    const float* x1p = p.img1 + off;
+                    const float* x2p = p.img2 + off;
+                    float* d1 = p.out0 + off;
+                    float* d2 = (NC == 4 && p.out1) ? p.out1 + off : nullptr;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (row0 + i < S1) {
+                            const float x1 = __ldg(x1p), x2 = __ldg(x2p);
+                            *d1 = g * (acc[0][i] + 2.f * x1 * acc[1][i] + x2 * acc[2][i]);
+                            if (NC == 4 && d2) *d2 = g * (acc[NC - 1][i] + 2.f * x2 * acc[1][i] + x1 * acc[2][i]);
+                        }
+                        x1p += W; x2p += W; d1 += W;
+                        if (NC == 4 && d2) d2 += W;
                     }
                 }
             }
         }
         __syncthreads();
-        // ---- carry the last 10 blurred rows to the top of the window
+        // ---- carry the last 10 blurred rows to the top of the window (ordered before the next vertical pass by
+        //      the barrier that follows the next cp.async wait)
         if (q + 1 < niter) {
-            for (int idx = tid; idx < NC * 2 * kHalo * kTW; idx += kThreads) {
-                const int m = idx / (2 * kHalo * kTW);
-                const int rem = idx - m * (2 * kHalo * kTW);
-                hbuf[m * kHR * kTW + rem] = hbuf[m * kHR * kTW + kCR * kTW + rem];
+            constexpr int N4 = NC * 2 * kHalo * kTW / 4;
+            for (int idx = tid; idx < N4; idx += kThreads) {
+                const int m = idx / (2 * kHalo * kTW / 4);
+                const int rem = idx - m * (2 * kHalo * kTW / 4);
+                float4* base = reinterpret_cast<float4*>(hbuf + m * kHR * kTW);
+                base[rem] = base[kCR * kTW / 4 + rem];
             }
-            // the next stage_rows / horizontal pass touch `stage` and hbuf rows >= 10 only; the barrier
-            // after stage_rows orders this copy before the next vertical pass
         }
     }
 
@@ -277,7 +299,7 @@ static void plan_grid(int planes, int H, int W, int* strips, int* nseg, int* seg
 template <bool FWD, int NC>
 static int launch_ssim(const SsimParams& p, cudaStream_t st) {
     constexpr int NI = FWD ? 2 : NC;
-    const size_t smem = sizeof(float) * (size_t)(NI * kCR * kPW + NC * kHR * kTW);
+    const size_t smem = sizeof(float) * (size_t)(2 * NI * kCR * kPW + NC * kHR * kTW);
     auto kern = ssim_stream_kernel<FWD, NC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_last_cuda_error(e);
@@ -286,6 +308,8 @@ static int launch_ssim(const SsimParams& p, cudaStream_t st) {
     e = cudaGetLastError();
     return e == cudaSuccess ? B200W_OK : set_last_cuda_error(e);
 }
+
+static bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
 
 static int fill_window(SsimParams& p, const float* win, int ws) {
     if (!win || ws < 1 || ws > kWin || (ws % 2) == 0) return B200W_ERR_BAD_WINDOW;
@@ -331,6 +355,7 @@ extern "C" int b200w_ssim_fwd_f32(const float* img1, const float* img2, int N, i
     p.map_stride = (long long)p.planes * H * W;
     p.n_maps = n_maps;
     p.size_average = size_average ? 1 : 0;
+    p.vec_ok = ((W % 4) == 0 && aligned16(img1) && aligned16(img2)) ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     rc = launch_ssim<true, 5>(p, st);
     if (rc) return rc;
@@ -368,6 +393,7 @@ extern "C" int b200w_ssim_bwd_f32(const float* img1, const float* img2, const fl
     p.n_maps = n_maps;
     p.size_average = size_average ? 1 : 0;
     p.inv_count = size_average ? (float)(1.0 / ((double)N * C * H * W)) : (float)(1.0 / ((double)C * H * W));
+    p.vec_ok = ((W % 4) == 0 && aligned16(maps)) ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (d2) return launch_ssim<false, 4>(p, st);
     return launch_ssim<false, 3>(p, st);
