@@ -1,0 +1,48 @@
+"""Make the reference's import names resolve to this package.
+
+    import b200wave.compat; b200wave.compat.install()
+    from pytorch_wavelets import DWTForward, DWTInverse      # -> b200wave.DWTForward / DWTInverse
+    import pytorch_wavelets.dwt.lowlevel as lowlevel          # -> b200wave.dwt.lowlevel
+    import ssim; ssim.SSIM()                                  # -> b200wave.ssim
+
+so that ``model.py`` (``from pytorch_wavelets import DWTForward, DWTInverse``, model.py:4) and ``train.py``
+(``import ssim``-style use at train.py:97) of the reference run unmodified on the CUDA path.  Only the 2-D DWT
+surface is provided (SURVEY.md section 2 marks the 1-D / SWT / DTCWT / scattering parts out of scope); asking
+for anything else raises AttributeError instead of silently falling back.
+"""
+import importlib
+import sys
+import types
+
+
+def install(force=False):
+    import b200wave
+    from b200wave.dwt import lowlevel, transform2d
+    ssim_mod = importlib.import_module("b200wave.ssim")
+
+    if not force:
+        for name in ("pytorch_wavelets", "ssim"):
+            mod = sys.modules.get(name)
+            if mod is not None and not getattr(mod, "__b200wave_alias__", False):
+                raise RuntimeError("module %r is already imported from %s; call install(force=True) to shadow it"
+                                   % (name, getattr(mod, "__file__", "?")))
+
+    pw = types.ModuleType("pytorch_wavelets")
+    pw.__b200wave_alias__ = True
+    pw.__version__ = "1.3.0+b200wave." + b200wave.__version__
+    pw.__path__ = []
+    for name in ("DWTForward", "DWTInverse", "DWT", "IDWT", "DWT2D", "IDWT2D"):
+        setattr(pw, name, getattr(b200wave, name))
+    dwt = types.ModuleType("pytorch_wavelets.dwt")
+    dwt.__b200wave_alias__ = True
+    dwt.__path__ = []
+    dwt.lowlevel = lowlevel
+    dwt.transform2d = transform2d
+    pw.dwt = dwt
+    sys.modules["pytorch_wavelets"] = pw
+    sys.modules["pytorch_wavelets.dwt"] = dwt
+    sys.modules["pytorch_wavelets.dwt.lowlevel"] = lowlevel
+    sys.modules["pytorch_wavelets.dwt.transform2d"] = transform2d
+    ssim_mod.__b200wave_alias__ = True
+    sys.modules["ssim"] = ssim_mod
+    return pw

@@ -127,3 +127,24 @@ def test_shard_range_covers_everything():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_compat_aliases_resolve_reference_imports():
+    import sys
+    import b200wave.compat
+    saved = {k: sys.modules.get(k) for k in ("pytorch_wavelets", "pytorch_wavelets.dwt", "ssim",
+                                              "pytorch_wavelets.dwt.lowlevel", "pytorch_wavelets.dwt.transform2d")}
+    try:
+        b200wave.compat.install(force=True)
+        from pytorch_wavelets import DWTForward, DWTInverse, IDWT
+        import pytorch_wavelets.dwt.lowlevel as ll
+        import ssim as ssim_alias
+        assert DWTForward is b200wave.DWTForward and IDWT is DWTInverse
+        assert ll.AFB2D is lowlevel.AFB2D and ll.mode_to_int("reflect") == 4
+        assert ssim_alias.SSIM is b200wave.SSIM and callable(ssim_alias.ssim)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
