@@ -10,6 +10,8 @@ import threading
 from . import _build
 
 _c_float_p = ctypes.POINTER(ctypes.c_float)
+_c_int_p = ctypes.POINTER(ctypes.c_int)
+_c_vp_p = ctypes.POINTER(ctypes.c_void_p)
 
 # status codes of include/b200wave.h
 OK = 0
@@ -25,6 +27,7 @@ ERR_BAD_WINDOW = -9
 
 ABI_VERSION = 1
 MAX_TAPS = 64
+MAX_LEVELS = 8
 SSIM_MAX_WINDOW = 11
 
 # every symbol the header declares: name -> (restype, argtypes)
@@ -41,6 +44,13 @@ SYMBOLS = {
     "b200w_sfb2d_f32": (_i, [_vp, _i64, _i64, _vp, _i, _i, _i,
                              _c_float_p, _c_float_p, _i, _c_float_p, _c_float_p, _i,
                              _i, _vp, _i, _i, _vp]),
+    "b200w_dwt2_workspace_bytes": (_sz, [_i, _i]),
+    "b200w_dwt2_f32": (_i, [_vp, _i64, _i64, _i, _i, _i,
+                            _c_float_p, _c_float_p, _i, _c_float_p, _c_float_p, _i,
+                            _i, _i, _c_int_p, _c_vp_p, _c_vp_p, _vp, _sz, _vp]),
+    "b200w_idwt2_f32": (_i, [_vp, _i64, _i64, _c_vp_p, _i, _c_int_p, _c_int_p,
+                             _c_float_p, _c_float_p, _i, _c_float_p, _c_float_p, _i,
+                             _i, _i, _c_int_p, _c_int_p, _c_vp_p, _vp, _sz, _vp]),
     "b200w_ssim_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "b200w_ssim_fwd_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _c_float_p, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "b200w_ssim_bwd_f32": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _c_float_p, _i, _i, _vp, _vp, _vp]),
@@ -92,6 +102,17 @@ def status_string(code):
 def taps_array(values):
     vals = [float(v) for v in values]
     return (ctypes.c_float * len(vals))(*vals), len(vals)
+
+
+def int_array(values):
+    vals = [int(v) for v in values]
+    return (ctypes.c_int * len(vals))(*vals)
+
+
+def ptr_array(tensors):
+    """HOST array of device pointers; None entries become NULL."""
+    vals = [None if t is None else t.data_ptr() for t in tensors]
+    return (ctypes.c_void_p * len(vals))(*vals)
 
 
 def check(code, mode_name=None):

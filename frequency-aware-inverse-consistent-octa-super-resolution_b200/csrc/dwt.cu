@@ -1,12 +1,18 @@
-// 2-D DWT analysis / synthesis levels for sm_100a.
+// 2-D DWT analysis / synthesis filter banks for sm_100a: one persistent kernel per multi-level transform.
 //
-// One fused kernel per level (BASELINE.json north_star): the analysis kernel stages an input tile
-// with its halo in shared memory (the padding mode is applied as an index map while staging), runs
-// the row (W) pass with stride-2 decimation into shared memory, then the column (H) pass, and writes
-// LL into `low` and LH/HL/HH straight into `highs[:, :, 0..2]` -- replacing the reference's
-// pad-gather + 2x F.conv2d + reshape + 2x .contiguous() (pw/dwt/lowlevel.py:336-347).
-// The synthesis kernel fuses upsample + filter + accumulate of all four sub-bands in polyphase form,
-// replacing 6x F.conv_transpose2d + 3 adds (pw/dwt/lowlevel.py:671-680).
+// What it replaces.  Per level the reference runs pad-gather + 2x F.conv2d + reshape + 2x .contiguous()
+// (AFB2D, pw/dwt/lowlevel.py:336-347) resp. 6x F.conv_transpose2d + 3 adds (SFB2D, :671-680), and
+// DWTForward / DWTInverse loop over the J levels in Python (pw/dwt/transform2d.py:66-74, 134-148).
+// Here a J-level transform is ONE launch: a persistent grid walks an ordered list of tiles (all tiles of the
+// first level, then the next level, ...); a tile of level j+1 of image plane p starts as soon as every tile of
+// level j of that plane has been written (per-plane completion counters, release/acquire), so levels overlap,
+// there are no launch gaps between the small coarse levels, and the LL intermediates are consumed out of L2.
+//
+// Per tile, analysis: the input patch (+halo) is staged in shared memory with cp.async -- the padding mode is
+// an index map applied to the source address -- double buffered so the next tile's fetch overlaps this tile's
+// arithmetic; row (W) pass with stride-2 decimation into shared memory; column (H) pass; LL goes to `low`,
+// LH/HL/HH straight into `highs[:, :, 0..2]`.  Synthesis is the polyphase mirror image (upsample + filter +
+// accumulate of all four sub-bands fused).
 //
 // Closed forms (validated against the reference to 1e-15 by oracle/dwt_oracle.py):
 //   analysis   y_c[k] = sum_j w_c[j] * x_ext[2k + j - off],  off = p//2 with p = 2(M-1) - N + L,
@@ -15,99 +21,203 @@
 //              off = L-2 (coefficients outside [0,M) are zero), periodization: off = L//2 - 1 and the
 //              coefficient sequence is M-periodic
 //
-// These are HBM-bound stencils (8 B of traffic per pixel for 2L FMAs): the kernels are organised to keep
-// the instruction count per pixel low -- 128-bit shared-memory loads feeding register-blocked FMAs whose
-// coefficients come from the constant bank, 64-bit coalesced global stores, and a staging loop in which
-// every thread owns one vector column of the tile so that addresses advance by a constant.
+// These are HBM-bound stencils (8 B of traffic per pixel for 2L FMAs): the code keeps the instruction count
+// per pixel low -- 128-bit shared loads feeding register-blocked FMAs whose coefficients come from the
+// constant bank, 64-bit coalesced global stores, staging loops whose addresses advance by constants.
 #include "common.cuh"
 
 namespace b200w {
 
-// Persistent tile schedule: CTA b handles tiles b, b+G, b+2G, ... of the (plane, tile_h, tile_w) space, w fastest,
-// so that CTAs running at the same time work on neighbouring tiles (halo re-reads hit L2).  The step G is
-// pre-decomposed on the host so the per-tile update needs no division.
-struct TileSched {
-    long long total;
-    int tiles_w, tiles_h;
-    int d_w, d_h, d_p;  // G = (d_p * tiles_h + d_h) * tiles_w + d_w
+constexpr int kMaxLevels = B200W_MAX_LEVELS;
+
+// ------------------------------------------------------------------------------------------------
+// chain bookkeeping shared by the analysis and the synthesis kernels
+// ------------------------------------------------------------------------------------------------
+struct TileRef {
+    int level, plane, th, tw;
 };
 
-struct TileIter {
-    long long tile;
-    int tw, th, plane;
-    __device__ __forceinline__ void init(const TileSched& s) {
-        tile = blockIdx.x;
-        tw = (int)(tile % s.tiles_w);
-        const long long t2 = tile / s.tiles_w;
-        th = (int)(t2 % s.tiles_h);
-        plane = (int)(t2 / s.tiles_h);
-    }
-    __device__ __forceinline__ void next(const TileSched& s) {
-        tile += gridDim.x;
-        tw += s.d_w;
-        if (tw >= s.tiles_w) { tw -= s.tiles_w; ++th; }
-        th += s.d_h;
-        if (th >= s.tiles_h) { th -= s.tiles_h; ++plane; }
-        plane += s.d_p;
-    }
-};
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
-struct AfbParams {
+// make this CTA's global stores (ordered before by a barrier) visible, then count the tile
+__device__ __forceinline__ void signal_done(unsigned* counter) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+}
+
+struct AfbLevel {
     const float* x;
     float* low;
     float* highs;
     long long x_ps, x_rs;
-    int planes, H, W, Ho, Wo;
-    int mode, offW, offH, Lw, Lh;
-    int in_vec;     // widest aligned vector (1, 2 or 4 floats) usable for staging copies
-    int out_vec2;   // 64-bit stores allowed (Wo even, 8 B aligned bases)
-    TileSched sched;
+    long long tile_base;   // index of this level's first tile in the global tile order
+    int H, W;              // logical input size (including the zero extension below)
+    int Hreal, Wreal;      // rows / columns >= these read as zero (SFB2D.backward through the 'unpad' crop)
+    int Ho, Wo;
+    int offH, offW;
+    int tiles_h, tiles_w;
+    int in_vec;            // widest aligned vector (1, 2 or 4 floats) usable for staging copies
+    int out_vec2;          // 64-bit stores allowed
+};
+
+struct AfbParams {
+    AfbLevel lv[kMaxLevels];
+    long long total;       // tiles over all levels
+    unsigned* done;        // [J][planes] completed-tile counters (null when J == 1)
+    int J, planes, mode;
     Taps t;
+};
+
+struct SfbLevel {
+    const float* low;
+    const float* highs;    // may be null (= zeros)
+    float* y;
+    long long low_ps, low_rs;
+    long long tile_base;
+    int h, w, out_h, out_w;
+    int offH, offW;
+    int a0H, a0W;          // first A-space coordinate (even) covered by tile 0
+    int tiles_h, tiles_w;
+    int in_vec2;           // 64-bit staging copies allowed
+    int out_vec2;          // 64-bit stores allowed
 };
 
 struct SfbParams {
-    const float* low;
-    const float* highs;  // may be null (= zeros)
-    float* y;
-    long long low_ps, low_rs;
-    int planes, h, w, out_h, out_w;
-    int periodic, offW, offH, Lw, Lh;
-    int a0W, a0H;  // first A-space coordinate (even) covered by tile 0
-    int in_vec2;   // 64-bit staging copies allowed
-    int out_vec2;  // 64-bit stores allowed
-    TileSched sched;
+    SfbLevel lv[kMaxLevels];  // chain order: coarsest level first
+    long long total;
+    unsigned* done;
+    int J, planes, periodic;
     Taps t;
 };
 
-__device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+template <class P>
+__device__ __forceinline__ TileRef decode_tile(const P& p, long long tile) {
+    int level = 0;
+    for (int j = 1; j < p.J; ++j)
+        if (tile >= p.lv[j].tile_base) level = j;
+    const unsigned local = (unsigned)(tile - p.lv[level].tile_base);
+    const unsigned ntw = (unsigned)p.lv[level].tiles_w;
+    const unsigned tpp = ntw * (unsigned)p.lv[level].tiles_h;
+    TileRef t;
+    t.level = level;
+    t.plane = (int)(local / tpp);
+    const unsigned rem = local - (unsigned)t.plane * tpp;
+    t.th = (int)(rem / ntw);
+    t.tw = (int)(rem - (unsigned)t.th * ntw);
+    return t;
+}
+
+// has every tile of the previous level of this plane been written?
+template <class P>
+__device__ __forceinline__ bool tile_ready(const P& p, const TileRef& t) {
+    if (t.level == 0) return true;
+    const unsigned need = (unsigned)(p.lv[t.level - 1].tiles_w * p.lv[t.level - 1].tiles_h);
+    return ld_acquire_u32(p.done + (size_t)(t.level - 1) * p.planes + t.plane) >= need;
+}
+
+// Persistent, double-buffered walk over the tile list.  Op provides the tile body:
+//   issue(p, tile, shared-window address of the staging buffer, tid)   cp.async the tile's inputs
+//   pass1(p, tile, staging buffer, scratch, tid)                        first 1-D pass, shared -> shared
+//   pass2(p, tile, scratch, tid)                                        second 1-D pass + global stores
+template <class Op>
+__global__ void __launch_bounds__(Op::NT) chain_kernel(const __grid_constant__ typename Op::Params p) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ int s_pf_ok;
+    float* scratch = smem + 2 * Op::BUF;   // two staging buffers come first
+    const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem);
+    const int tid = threadIdx.x;
+    const long long G = gridDim.x;
+
+    long long tile = blockIdx.x;
+    if (tile >= p.total) return;
+    TileRef cur = decode_tile(p, tile), nxt = cur;
+    if (cur.level > 0) {   // only when the grid is larger than the first level
+        if (tid == 0)
+            while (!tile_ready(p, cur)) __nanosleep(64);
+        __syncthreads();
+    }
+    Op::issue(p, cur, smem_s, tid);
+    cp_async_commit();
+    // prefetch decision for the following tile; later ones are made by thread 0 inside the loop
+    int pf_ok = (tile + G < p.total) && (tile + G < (p.J > 1 ? p.lv[1].tile_base : p.total));
+    int pend_level = -1, pend_plane = 0;   // tile whose completion still has to be published
+
+    for (int buf = 0;; buf ^= 1) {
+        cp_async_wait<0>();   // this thread's copies of the current tile have landed ...
+        __syncthreads();      // ... and everybody else's; the previous tile's stores are ordered before this barrier
+        // publish the previous tile BEFORE this thread has copies in flight again (the fence waits for them)
+        if (tid == 0 && pend_level >= 0) signal_done(p.done + (size_t)pend_level * p.planes + pend_plane);
+        const long long ntile = tile + G;
+        const bool have_next = ntile < p.total;
+        bool prefetched = false;
+        if (have_next) {
+            nxt = decode_tile(p, ntile);
+            if (pf_ok) {   // the next tile's inputs are complete: fetch them while this tile is processed
+                Op::issue(p, nxt, smem_s + (unsigned)((buf ^ 1) * Op::BUF * 4), tid);
+                prefetched = true;
+            }
+        }
+        cp_async_commit();
+        // thread 0 probes whether the tile after next will be fetchable; the load stays in flight across pass1
+        unsigned dep_have = 1, dep_need = 0;
+        if (tid == 0) {
+            const long long nn = ntile + G;
+            if (nn >= p.total) {
+                dep_have = 0;
+                dep_need = 1;
+            } else {
+                const TileRef t2 = decode_tile(p, nn);
+                if (t2.level > 0) {
+                    dep_need = (unsigned)(p.lv[t2.level - 1].tiles_w * p.lv[t2.level - 1].tiles_h);
+                    dep_have = ld_acquire_u32(p.done + (size_t)(t2.level - 1) * p.planes + t2.plane);
+                }
+            }
+        }
+        Op::pass1(p, cur, smem + buf * Op::BUF, scratch, tid);
+        if (tid == 0) s_pf_ok = dep_have >= dep_need ? 1 : 0;
+        __syncthreads();
+        Op::pass2(p, cur, scratch, tid);
+        pf_ok = s_pf_ok;
+        const bool has_consumer = cur.level + 1 < p.J;
+        pend_level = has_consumer ? cur.level : -1;
+        pend_plane = cur.plane;
+        if (!have_next) break;
+        if (!prefetched) {
+            // the next tile's inputs were not complete when we looked: publish our own result first (it may be
+            // the missing piece), then wait for the producers -- all of them own earlier tiles and are resident
+            __syncthreads();
+            if (tid == 0) {
+                if (pend_level >= 0) signal_done(p.done + (size_t)pend_level * p.planes + pend_plane);
+                while (!tile_ready(p, nxt)) __nanosleep(64);
+            }
+            pend_level = -1;
+            __syncthreads();
+            Op::issue(p, nxt, smem_s + (unsigned)((buf ^ 1) * Op::BUF * 4), tid);
+            cp_async_commit();
+        }
+        tile = ntile;
+        cur = nxt;
+    }
+    if (pend_level >= 0) {
+        __syncthreads();
+        if (tid == 0) signal_done(p.done + (size_t)pend_level * p.planes + pend_plane);
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
-// analysis, tiled + persistent.  Output tile TH x TW per iteration (x4 sub-bands), NT threads.
+// analysis tile.  Output tile TH x TW (x4 sub-bands), NT threads.
 // ------------------------------------------------------------------------------------------------
-template <int L, int TW, int TH, int NT>
-struct AfbCfg {
-    static constexpr int PC = 2 * TW + L - 2;     // staged patch columns actually needed
-    static constexpr int PCP = (PC + 3) & ~3;     // row pitch (multiple of 4 floats: 128-bit LDS)
-    static constexpr int PR = 2 * TH + L - 2;     // staged patch rows
-    static constexpr int NP = TW / 2;             // output pairs per row (row pass)
-    static constexpr int RSTEP = NT / NP;         // patch rows advanced per row-pass iteration
-    static constexpr int NV = (L + 2 + 3) / 4;    // float4 loads per row-pass item
-    static constexpr int CP = TW / 2;             // column pairs (column pass)
-    static constexpr int NS = NT / CP;            // row strips in the column pass
-    static constexpr int RS = TH / NS;            // output rows per thread in the column pass
-    static constexpr size_t smem = sizeof(float) * (size_t)(2 * PR * PCP + 2 * PR * TW);  // 2 patches + mid
-    static_assert(L % 2 == 0 && TW % 4 == 0 && NT % CP == 0 && TH % NS == 0 && NT % NP == 0, "bad tile");
-    static_assert(2 * TW - 4 + 4 * NV <= PCP, "row pass would read past the patch row");
-    static_assert(PCP <= NT, "staging needs one thread per scalar column");
-};
-
 // Stage ROWS x PITCH floats asynchronously.  Every thread owns one vector column (V floats) and walks down
 // the rows, so both addresses advance by constants.  (r0, c0) = source coordinates of patch element (0,0);
-// the padding mode is applied as an index map, "zero" = zero fill.
+// the padding mode is applied as an index map, "zero" = zero fill (cp.async with src-size 0).
 template <int V, int ROWS, int PITCH, int NT>
 __device__ __forceinline__ void stage_analysis(unsigned patch_s, const float* __restrict__ xp, long long rs, int r0,
-                                               int c0, int H, int W, int mode, int nrows, int ncols, int tid) {
+                                               int c0, int H, int W, int Hreal, int Wreal, int mode, int nrows,
+                                               int ncols, int tid) {
     constexpr int NVC = PITCH / V;   // vector columns per row
     constexpr int NRG = NT / NVC;    // row groups
     if (tid >= NVC * NRG) return;
@@ -115,9 +225,9 @@ __device__ __forceinline__ void stage_analysis(unsigned patch_s, const float* __
     const int rg = tid / NVC;
     if (V * cv >= ncols) return;     // columns that feed no valid output of an edge tile are not staged
     const int sc0 = c0 + V * cv;
-    const bool col_in = sc0 >= 0 && sc0 + V <= W;
+    const bool col_in = sc0 >= 0 && sc0 + V <= Wreal;
     unsigned dst = patch_s + (unsigned)((rg * PITCH + V * cv) * 4);
-    if (col_in && r0 >= 0 && r0 + nrows <= H) {
+    if (col_in && r0 >= 0 && r0 + nrows <= Hreal) {
         const float* src = xp + (long long)(r0 + rg) * rs + sc0;
         const long long step = (long long)NRG * rs;
 #pragma unroll 4
@@ -130,10 +240,13 @@ __device__ __forceinline__ void stage_analysis(unsigned patch_s, const float* __
     }
     int ci[V];
 #pragma unroll
-    for (int e = 0; e < V; ++e) ci[e] = ext_index(sc0 + e, W, mode);
+    for (int e = 0; e < V; ++e) {
+        ci[e] = ext_index(sc0 + e, W, mode);
+        if (ci[e] >= Wreal) ci[e] = -1;
+    }
     for (int r = rg; r < nrows; r += NRG, dst += NRG * PITCH * 4) {
         const int sr = ext_index(r0 + r, H, mode);
-        if (sr < 0) {
+        if (sr < 0 || sr >= Hreal) {
             cp_async_zero<V>(dst, xp);
             continue;
         }
@@ -147,153 +260,156 @@ __device__ __forceinline__ void stage_analysis(unsigned patch_s, const float* __
     }
 }
 
-template <int L, int TW, int TH, int NT>
-__device__ __forceinline__ void afb_issue(unsigned patch_s, const AfbParams& p, const TileIter& it, int tid) {
-    using Cfg = AfbCfg<L, TW, TH, NT>;
-    const int r0 = 2 * it.th * TH - p.offH;  // source row of patch row 0
-    const int c0 = 2 * it.tw * TW - p.offW;
-    const float* xp = p.x + (long long)it.plane * p.x_ps;
-    // an edge tile only needs the rows / columns its valid outputs read: 2*(n_valid-1) + L of them
-    const int nrows = min(Cfg::PR, 2 * (min(TH, p.Ho - it.th * TH) - 1) + L);
-    const int ncols = min(Cfg::PCP, 2 * (min(TW, p.Wo - it.tw * TW) - 1) + L);
-    if (p.in_vec == 4) stage_analysis<4, Cfg::PR, Cfg::PCP, NT>(patch_s, xp, p.x_rs, r0, c0, p.H, p.W, p.mode, nrows, ncols, tid);
-    else if (p.in_vec == 2) stage_analysis<2, Cfg::PR, Cfg::PCP, NT>(patch_s, xp, p.x_rs, r0, c0, p.H, p.W, p.mode, nrows, ncols, tid);
-    else stage_analysis<1, Cfg::PR, Cfg::PCP, NT>(patch_s, xp, p.x_rs, r0, c0, p.H, p.W, p.mode, nrows, ncols, tid);
-}
+template <int L_, int TW_, int TH_, int NT_>
+struct AfbOp {
+    using Params = AfbParams;
+    static constexpr int L = L_, TW = TW_, TH = TH_, NT = NT_;
+    static constexpr int PC = 2 * TW + L - 2;     // staged patch columns actually needed
+    static constexpr int PCP = (PC + 3) & ~3;     // row pitch (multiple of 4 floats: 128-bit LDS)
+    static constexpr int PR = 2 * TH + L - 2;     // staged patch rows
+    static constexpr int BUF = PR * PCP;          // floats per staging buffer
+    static constexpr int NP = TW / 2;             // output pairs per row (row pass)
+    static constexpr int RSTEP = NT / NP;         // patch rows advanced per row-pass iteration
+    static constexpr int NV = (L + 2 + 3) / 4;    // float4 loads per row-pass item
+    static constexpr int CP = TW / 2;             // column pairs (column pass)
+    static constexpr int NS = NT / CP;            // row strips in the column pass
+    static constexpr int RS = TH / NS;            // output rows per thread in the column pass
+    static constexpr size_t smem = sizeof(float) * (size_t)(2 * BUF + 2 * PR * TW);  // 2 patches + mid_lo/mid_hi
+    static_assert(L % 2 == 0 && TW % 4 == 0 && NT % CP == 0 && TH % NS == 0 && NT % NP == 0, "bad tile");
+    static_assert(2 * TW - 4 + 4 * NV <= PCP, "row pass would read past the patch row");
+    static_assert(PCP <= NT, "staging needs one thread per scalar column");
 
-template <int L, int TW, int TH, int NT>
-__global__ void __launch_bounds__(NT) afb2d_tile_kernel(const __grid_constant__ AfbParams p) {
-    using Cfg = AfbCfg<L, TW, TH, NT>;
-    constexpr int PCP = Cfg::PCP, PR = Cfg::PR, NP = Cfg::NP, NV = Cfg::NV, CP = Cfg::CP, RS = Cfg::RS,
-                  RSTEP = Cfg::RSTEP;
-    extern __shared__ __align__(16) float smem[];
-    float* mid_lo = smem + 2 * PR * PCP;  // [PR][TW]   (two patch buffers [PR][PCP] come first)
-    float* mid_hi = mid_lo + PR * TW;     // [PR][TW]
-    const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem);
+    static __device__ __forceinline__ void issue(const AfbParams& p, const TileRef& t, unsigned patch_s, int tid) {
+        const AfbLevel& lv = p.lv[t.level];
+        const int r0 = 2 * t.th * TH - lv.offH;  // source row of patch row 0
+        const int c0 = 2 * t.tw * TW - lv.offW;
+        const float* xp = lv.x + (long long)t.plane * lv.x_ps;
+        // an edge tile only needs the rows / columns its valid outputs read: 2*(n_valid-1) + L of them
+        const int nrows = min(PR, 2 * (min(TH, lv.Ho - t.th * TH) - 1) + L);
+        const int ncols = min(PCP, 2 * (min(TW, lv.Wo - t.tw * TW) - 1) + L);
+        if (lv.in_vec == 4)
+            stage_analysis<4, PR, PCP, NT>(patch_s, xp, lv.x_rs, r0, c0, lv.H, lv.W, lv.Hreal, lv.Wreal, p.mode, nrows, ncols, tid);
+        else if (lv.in_vec == 2)
+            stage_analysis<2, PR, PCP, NT>(patch_s, xp, lv.x_rs, r0, c0, lv.H, lv.W, lv.Hreal, lv.Wreal, p.mode, nrows, ncols, tid);
+        else
+            stage_analysis<1, PR, PCP, NT>(patch_s, xp, lv.x_rs, r0, c0, lv.H, lv.W, lv.Hreal, lv.Wreal, p.mode, nrows, ncols, tid);
+    }
 
-    const int tid = threadIdx.x;
-    TileIter it, nx;
-    it.init(p.sched);
-    nx = it;
-    afb_issue<L, TW, TH, NT>(smem_s, p, it, tid);  // prologue: start fetching the first tile
-    cp_async_commit();
-
-    for (int buf = 0; it.tile < p.sched.total; buf ^= 1, it = nx) {
-        const float* patch = smem + buf * (PR * PCP);
-        // prefetch this CTA's next tile into the other buffer while the current one is processed
-        nx.next(p.sched);
-        if (nx.tile < p.sched.total) afb_issue<L, TW, TH, NT>(smem_s + (unsigned)((buf ^ 1) * (PR * PCP * 4)), p, nx, tid);
-        cp_async_commit();
-        cp_async_wait<1>();  // this thread's copies of the current tile have landed ...
-        __syncthreads();     // ... and everybody else's; also orders the previous tile's column pass before mid_* is rewritten
-
-        // ---- row pass (along W), decimate by 2: each item makes two adjacent outputs of one patch row from
-        //      NV 128-bit shared loads (conflict free: consecutive lanes read consecutive float4)
-        {
-            const int kk = tid % NP;
-            int r = tid / NP;
-            const float* src = patch + r * PCP + 4 * kk;
-            float* dlo = mid_lo + r * TW + 2 * kk;
+    // row pass (along W), decimate by 2: each item makes two adjacent outputs of one patch row from NV 128-bit
+    // shared loads (conflict free: consecutive lanes read consecutive float4)
+    static __device__ __forceinline__ void pass1(const AfbParams& p, const TileRef&, const float* patch, float* mid,
+                                                 int tid) {
+        const int kk = tid % NP;
+        int r = tid / NP;
+        const float* src = patch + r * PCP + 4 * kk;
+        float* dlo = mid + r * TW + 2 * kk;
 #pragma unroll 2
-            for (; r < PR; r += RSTEP, src += RSTEP * PCP, dlo += RSTEP * TW) {
-                float v[4 * NV];
+        for (; r < PR; r += RSTEP, src += RSTEP * PCP, dlo += RSTEP * TW) {
+            float v[4 * NV];
 #pragma unroll
-                for (int q = 0; q < NV; ++q) {
-                    const float4 t = reinterpret_cast<const float4*>(src)[q];
-                    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-                }
-                float lo0 = 0.f, hi0 = 0.f, lo1 = 0.f, hi1 = 0.f;
+            for (int q = 0; q < NV; ++q) {
+                const float4 t = reinterpret_cast<const float4*>(src)[q];
+                v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+            }
+            float lo0 = 0.f, hi0 = 0.f, lo1 = 0.f, hi1 = 0.f;
 #pragma unroll
-                for (int j = 0; j < L; ++j) {
-                    lo0 = fmaf(p.t.w_lo[j], v[j], lo0);
-                    hi0 = fmaf(p.t.w_hi[j], v[j], hi0);
-                    lo1 = fmaf(p.t.w_lo[j], v[j + 2], lo1);
-                    hi1 = fmaf(p.t.w_hi[j], v[j + 2], hi1);
+            for (int j = 0; j < L; ++j) {
+                lo0 = fmaf(p.t.w_lo[j], v[j], lo0);
+                hi0 = fmaf(p.t.w_hi[j], v[j], hi0);
+                lo1 = fmaf(p.t.w_lo[j], v[j + 2], lo1);
+                hi1 = fmaf(p.t.w_hi[j], v[j + 2], hi1);
+            }
+            *reinterpret_cast<float2*>(dlo) = make_float2(lo0, lo1);
+            *reinterpret_cast<float2*>(dlo + PR * TW) = make_float2(hi0, hi1);
+        }
+    }
+
+    // column pass (along H), decimate by 2; each thread owns RS output rows of two adjacent columns
+    static __device__ __forceinline__ void pass2(const AfbParams& p, const TileRef& t, const float* mid, int tid) {
+        const AfbLevel& lv = p.lv[t.level];
+        const int cp = tid % CP;
+        const int s = tid / CP;
+        float2 acc[RS][4];
+#pragma unroll
+        for (int i = 0; i < RS; ++i)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[i][b] = make_float2(0.f, 0.f);
+        const float2* plo = reinterpret_cast<const float2*>(mid + (2 * s * RS) * TW + 2 * cp);
+        const float2* phi = reinterpret_cast<const float2*>(mid + PR * TW + (2 * s * RS) * TW + 2 * cp);
+#pragma unroll
+        for (int rr = 0; rr < 2 * RS + L - 2; ++rr) {
+            const float2 vlo = plo[rr * (TW / 2)];
+            const float2 vhi = phi[rr * (TW / 2)];
+#pragma unroll
+            for (int i = 0; i < RS; ++i) {
+                const int j = rr - 2 * i;
+                if (j >= 0 && j < L) {
+                    const float a = p.t.h_lo[j], b = p.t.h_hi[j];
+                    acc[i][0].x = fmaf(a, vlo.x, acc[i][0].x); acc[i][0].y = fmaf(a, vlo.y, acc[i][0].y);  // LL
+                    acc[i][1].x = fmaf(b, vlo.x, acc[i][1].x); acc[i][1].y = fmaf(b, vlo.y, acc[i][1].y);  // LH: W-lo, H-hi
+                    acc[i][2].x = fmaf(a, vhi.x, acc[i][2].x); acc[i][2].y = fmaf(a, vhi.y, acc[i][2].y);  // HL: W-hi, H-lo
+                    acc[i][3].x = fmaf(b, vhi.x, acc[i][3].x); acc[i][3].y = fmaf(b, vhi.y, acc[i][3].y);  // HH
                 }
-                *reinterpret_cast<float2*>(dlo) = make_float2(lo0, lo1);
-                *reinterpret_cast<float2*>(dlo + PR * TW) = make_float2(hi0, hi1);
             }
         }
-        __syncthreads();
-
-        // ---- column pass (along H), decimate by 2; each thread owns RS output rows of two adjacent columns
-        {
-            const int cp = tid % CP;
-            const int s = tid / CP;
-            float2 acc[RS][4];
+        const int Ho = lv.Ho, Wo = lv.Wo;
+        const int kk = t.tw * TW + 2 * cp;
+        const int row0 = t.th * TH + s * RS;
+        const size_t band = (size_t)Ho * Wo;
+        float* q0 = lv.low + (size_t)t.plane * band + (size_t)row0 * Wo + kk;
+        float* q1 = lv.highs + (size_t)t.plane * 3 * band + (size_t)row0 * Wo + kk;
+        float* q2 = q1 + band;
+        float* q3 = q2 + band;
+        if (lv.out_vec2 && row0 + RS <= Ho && kk + 1 < Wo) {  // whole strip inside: 64-bit stores
 #pragma unroll
-            for (int i = 0; i < RS; ++i)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) acc[i][b] = make_float2(0.f, 0.f);
-            const float2* plo = reinterpret_cast<const float2*>(mid_lo + (2 * s * RS) * TW + 2 * cp);
-            const float2* phi = reinterpret_cast<const float2*>(mid_hi + (2 * s * RS) * TW + 2 * cp);
-#pragma unroll
-            for (int rr = 0; rr < 2 * RS + L - 2; ++rr) {
-                const float2 vlo = plo[rr * (TW / 2)];
-                const float2 vhi = phi[rr * (TW / 2)];
-#pragma unroll
-                for (int i = 0; i < RS; ++i) {
-                    const int j = rr - 2 * i;
-                    if (j >= 0 && j < L) {
-                        const float a = p.t.h_lo[j], b = p.t.h_hi[j];
-                        acc[i][0].x = fmaf(a, vlo.x, acc[i][0].x); acc[i][0].y = fmaf(a, vlo.y, acc[i][0].y);  // LL
-                        acc[i][1].x = fmaf(b, vlo.x, acc[i][1].x); acc[i][1].y = fmaf(b, vlo.y, acc[i][1].y);  // LH
-                        acc[i][2].x = fmaf(a, vhi.x, acc[i][2].x); acc[i][2].y = fmaf(a, vhi.y, acc[i][2].y);  // HL
-                        acc[i][3].x = fmaf(b, vhi.x, acc[i][3].x); acc[i][3].y = fmaf(b, vhi.y, acc[i][3].y);  // HH
-                    }
-                }
+            for (int i = 0; i < RS; ++i) {
+                *reinterpret_cast<float2*>(q0) = acc[i][0];
+                *reinterpret_cast<float2*>(q1) = acc[i][1];
+                *reinterpret_cast<float2*>(q2) = acc[i][2];
+                *reinterpret_cast<float2*>(q3) = acc[i][3];
+                q0 += Wo; q1 += Wo; q2 += Wo; q3 += Wo;
             }
-            const int kk = it.tw * TW + 2 * cp;
-            const int row0 = it.th * TH + s * RS;
-            const size_t band = (size_t)p.Ho * p.Wo;
-            float* q0 = p.low + (size_t)it.plane * band + (size_t)row0 * p.Wo + kk;
-            float* q1 = p.highs + (size_t)it.plane * 3 * band + (size_t)row0 * p.Wo + kk;
-            float* q2 = q1 + band;
-            float* q3 = q2 + band;
-            if (p.out_vec2 && row0 + RS <= p.Ho && kk + 1 < p.Wo) {  // whole strip inside, 64-bit stores
+        } else if (kk < Wo) {
+            const bool second = kk + 1 < Wo;
 #pragma unroll
-                for (int i = 0; i < RS; ++i) {
-                    *reinterpret_cast<float2*>(q0) = acc[i][0];
-                    *reinterpret_cast<float2*>(q1) = acc[i][1];
-                    *reinterpret_cast<float2*>(q2) = acc[i][2];
-                    *reinterpret_cast<float2*>(q3) = acc[i][3];
-                    q0 += p.Wo; q1 += p.Wo; q2 += p.Wo; q3 += p.Wo;
+            for (int i = 0; i < RS; ++i) {
+                if (row0 + i < Ho) {
+                    q0[0] = acc[i][0].x; q1[0] = acc[i][1].x; q2[0] = acc[i][2].x; q3[0] = acc[i][3].x;
+                    if (second) { q0[1] = acc[i][0].y; q1[1] = acc[i][1].y; q2[1] = acc[i][2].y; q3[1] = acc[i][3].y; }
                 }
-            } else if (kk < p.Wo) {
-                const bool second = kk + 1 < p.Wo;
-#pragma unroll
-                for (int i = 0; i < RS; ++i) {
-                    if (row0 + i < p.Ho) {
-                        q0[0] = acc[i][0].x; q1[0] = acc[i][1].x; q2[0] = acc[i][2].x; q3[0] = acc[i][3].x;
-                        if (second) { q0[1] = acc[i][0].y; q1[1] = acc[i][1].y; q2[1] = acc[i][2].y; q3[1] = acc[i][3].y; }
-                    }
-                    q0 += p.Wo; q1 += p.Wo; q2 += p.Wo; q3 += p.Wo;
-                }
+                q0 += Wo; q1 += Wo; q2 += Wo; q3 += Wo;
             }
         }
     }
-}
+};
 
-// analysis, direct (any tap counts up to kMaxTaps, odd or mixed lengths): one thread per output
-// position, no staging.  Fallback and on-device cross-check of the tiled kernel.
-__global__ void __launch_bounds__(kThreads) afb2d_direct_kernel(const __grid_constant__ AfbParams p) {
-    const size_t band = (size_t)p.Ho * p.Wo;
+// analysis, direct (any tap counts up to kMaxTaps, odd or mixed lengths): one thread per output position of
+// ONE level, no staging.  Fallback and on-device cross-check of the tiled kernel.
+struct AfbDirectParams {
+    AfbLevel lv;
+    int planes, mode, Lw, Lh;
+    Taps t;
+};
+
+__global__ void __launch_bounds__(kThreads) afb2d_direct_kernel(const __grid_constant__ AfbDirectParams p) {
+    const AfbLevel& lv = p.lv;
+    const size_t band = (size_t)lv.Ho * lv.Wo;
     const size_t total = band * p.planes;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x) {
-        const int k = (int)(idx % p.Wo);
-        const int i = (int)((idx / p.Wo) % p.Ho);
+        const int k = (int)(idx % lv.Wo);
+        const int i = (int)((idx / lv.Wo) % lv.Ho);
         const int plane = (int)(idx / band);
-        const float* __restrict__ xp = p.x + (long long)plane * p.x_ps;
+        const float* __restrict__ xp = lv.x + (long long)plane * lv.x_ps;
         float ll = 0.f, lh = 0.f, hl = 0.f, hh = 0.f;
         for (int jh = 0; jh < p.Lh; ++jh) {
-            const int sr = ext_index(2 * i + jh - p.offH, p.H, p.mode);
-            if (sr < 0) continue;
+            const int sr = ext_index(2 * i + jh - lv.offH, lv.H, p.mode);
+            if (sr < 0 || sr >= lv.Hreal) continue;
             float lo = 0.f, hi = 0.f;
             for (int jw = 0; jw < p.Lw; ++jw) {
-                const int sc = ext_index(2 * k + jw - p.offW, p.W, p.mode);
-                if (sc < 0) continue;
-                const float v = __ldg(xp + (long long)sr * p.x_rs + sc);
+                const int sc = ext_index(2 * k + jw - lv.offW, lv.W, p.mode);
+                if (sc < 0 || sc >= lv.Wreal) continue;
+                const float v = __ldg(xp + (long long)sr * lv.x_rs + sc);
                 lo = fmaf(p.t.w_lo[jw], v, lo);
                 hi = fmaf(p.t.w_hi[jw], v, hi);
             }
@@ -302,9 +418,9 @@ __global__ void __launch_bounds__(kThreads) afb2d_direct_kernel(const __grid_con
             hl = fmaf(p.t.h_lo[jh], hi, hl);
             hh = fmaf(p.t.h_hi[jh], hi, hh);
         }
-        const size_t o = (size_t)i * p.Wo + k;
-        p.low[(size_t)plane * band + o] = ll;
-        float* hip = p.highs + (size_t)plane * 3 * band + o;
+        const size_t o = (size_t)i * lv.Wo + k;
+        lv.low[(size_t)plane * band + o] = ll;
+        float* hip = lv.highs + (size_t)plane * 3 * band + o;
         hip[0] = lh;
         hip[band] = hl;
         hip[2 * band] = hh;
@@ -312,29 +428,11 @@ __global__ void __launch_bounds__(kThreads) afb2d_direct_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------
-// synthesis, tiled + persistent.  Works in "A-space": a = n + off, so that the polyphase split (which taps
-// an output uses) depends only on the parity of the tile-local coordinate.  Output tile TH x TW.
-// W synthesis first (on the KH coefficient rows), then H synthesis; by separability this equals the
-// reference's H-then-W order (pw/dwt/lowlevel.py:677-679) up to fp32 rounding.
+// synthesis tile.  Works in "A-space": a = n + off, so that the polyphase split (which taps an output uses)
+// depends only on the parity of the tile-local coordinate.  Output tile TH x TW.  W synthesis first (on the KH
+// coefficient rows), then H synthesis; by separability this equals the reference's H-then-W order
+// (pw/dwt/lowlevel.py:677-679) up to fp32 rounding.
 // ------------------------------------------------------------------------------------------------
-template <int L, int TW, int TH, int NT>
-struct SfbCfg {
-    static constexpr int H2 = L / 2;
-    static constexpr int NV2 = (H2 + 2) / 2;            // float2 loads per band per W-synthesis item
-    static constexpr int KWP = TW / 2 - 2 + 2 * NV2;    // staged coefficient columns (even, >= TW/2 + H2 - 1)
-    static constexpr int KH = TH / 2 + H2 - 1;          // staged coefficient rows
-    static constexpr int PB = KH * KWP;                 // one band's patch
-    static constexpr int NQ = TW / 4;                   // W-synthesis items per coefficient row (4 outputs each)
-    static constexpr int QSTEP = NT / NQ;               // coefficient rows advanced per W-synthesis iteration
-    static constexpr int CP = TW / 2;                   // output column pairs (H pass)
-    static constexpr int NS = NT / CP;
-    static constexpr int RS = TH / NS;                  // output rows per thread in the H pass (even)
-    static constexpr int NR = RS / 2 + H2 - 1;          // coefficient rows feeding RS outputs
-    static constexpr size_t smem = sizeof(float) * (size_t)(2 * 4 * PB + 2 * KH * TW);  // 2 x 4 patches + u
-    static_assert(L % 2 == 0 && TW % 4 == 0 && NT % CP == 0 && TH % NS == 0 && RS % 2 == 0 && NT % NQ == 0, "bad tile");
-    static_assert(KWP >= TW / 2 + H2 - 1 && KWP % 2 == 0 && KWP <= NT, "bad KWP");
-};
-
 // Stage the 4 sub-band patches [4][KH][KWP] asynchronously; thread = one vector column, walking down the rows.
 // Coefficients outside the arrays are zero (or wrap for periodization); missing `highs` = zeros.
 template <int V, int KH, int KWP, int NT>
@@ -404,166 +502,170 @@ __device__ __forceinline__ void stage_synthesis(unsigned sub_s, const float* __r
     }
 }
 
-template <int L, int TW, int TH, int NT>
-__device__ __forceinline__ void sfb_issue(unsigned sub_s, const SfbParams& p, const TileIter& it, int tid) {
-    using Cfg = SfbCfg<L, TW, TH, NT>;
-    const int kW0 = (p.a0W + it.tw * TW) / 2 - (Cfg::H2 - 1);
-    const int kH0 = (p.a0H + it.th * TH) / 2 - (Cfg::H2 - 1);
-    const size_t band = (size_t)p.h * p.w;
-    const float* lowp = p.low + (long long)it.plane * p.low_ps;
-    const float* hip = p.highs ? p.highs + (size_t)it.plane * 3 * band : nullptr;
-    // coefficient rows / columns feeding the valid outputs of an edge tile: local a <= a_max -> k_local <= a_max/2 + H2-1
-    const int amax_h = min(TH - 1, p.offH + p.out_h - 1 - (p.a0H + it.th * TH));
-    const int amax_w = min(TW - 1, p.offW + p.out_w - 1 - (p.a0W + it.tw * TW));
-    const int nrows = min(Cfg::KH, amax_h / 2 + Cfg::H2);
-    const int ncols = min(Cfg::KWP, amax_w / 2 + Cfg::H2);
-    // kW0 is even whenever in_vec2 is set (checked on the host)
-    if (p.in_vec2) stage_synthesis<2, Cfg::KH, Cfg::KWP, NT>(sub_s, lowp, p.low_rs, hip, band, kH0, kW0, p.h, p.w, p.periodic, nrows, ncols, tid);
-    else stage_synthesis<1, Cfg::KH, Cfg::KWP, NT>(sub_s, lowp, p.low_rs, hip, band, kH0, kW0, p.h, p.w, p.periodic, nrows, ncols, tid);
-}
+template <int L_, int TW_, int TH_, int NT_>
+struct SfbOp {
+    using Params = SfbParams;
+    static constexpr int L = L_, TW = TW_, TH = TH_, NT = NT_;
+    static constexpr int H2 = L / 2;
+    static constexpr int NV2 = (H2 + 2) / 2;            // float2 loads per band per W-synthesis item
+    static constexpr int KWP = TW / 2 - 2 + 2 * NV2;    // staged coefficient columns (even, >= TW/2 + H2 - 1)
+    static constexpr int KH = TH / 2 + H2 - 1;          // staged coefficient rows
+    static constexpr int PB = KH * KWP;                 // one band's patch
+    static constexpr int BUF = 4 * PB;                  // floats per staging buffer (LL, LH, HL, HH)
+    static constexpr int NQ = TW / 4;                   // W-synthesis items per coefficient row (4 outputs each)
+    static constexpr int QSTEP = NT / NQ;               // coefficient rows advanced per W-synthesis iteration
+    static constexpr int CP = TW / 2;                   // output column pairs (H pass)
+    static constexpr int NS = NT / CP;
+    static constexpr int RS = TH / NS;                  // output rows per thread in the H pass (even)
+    static constexpr int NR = RS / 2 + H2 - 1;          // coefficient rows feeding RS outputs
+    static constexpr size_t smem = sizeof(float) * (size_t)(2 * BUF + 2 * KH * TW);  // 2 x 4 patches + u_lo/u_hi
+    static_assert(L % 2 == 0 && TW % 4 == 0 && NT % CP == 0 && TH % NS == 0 && RS % 2 == 0 && NT % NQ == 0, "bad tile");
+    static_assert(KWP >= TW / 2 + H2 - 1 && KWP % 2 == 0 && KWP <= NT, "bad KWP");
 
-template <int L, int TW, int TH, int NT>
-__global__ void __launch_bounds__(NT) sfb2d_tile_kernel(const __grid_constant__ SfbParams p) {
-    using Cfg = SfbCfg<L, TW, TH, NT>;
-    constexpr int H2 = Cfg::H2, NV2 = Cfg::NV2, KWP = Cfg::KWP, KH = Cfg::KH, PB = Cfg::PB, NQ = Cfg::NQ,
-                  QSTEP = Cfg::QSTEP, CP = Cfg::CP, RS = Cfg::RS, NR = Cfg::NR;
-    extern __shared__ __align__(16) float smem[];
-    float* u_lo = smem + 2 * 4 * PB;   // [KH][TW]  W-synthesised, to be combined with h_lo (2 patch sets first)
-    float* u_hi = u_lo + KH * TW;      // [KH][TW]  ... with h_hi
-    const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem);
+    static __device__ __forceinline__ void issue(const SfbParams& p, const TileRef& t, unsigned sub_s, int tid) {
+        const SfbLevel& lv = p.lv[t.level];
+        const int aW = lv.a0W + t.tw * TW, aH = lv.a0H + t.th * TH;
+        const int kW0 = aW / 2 - (H2 - 1);
+        const int kH0 = aH / 2 - (H2 - 1);
+        const size_t band = (size_t)lv.h * lv.w;
+        const float* lowp = lv.low + (long long)t.plane * lv.low_ps;
+        const float* hip = lv.highs ? lv.highs + (size_t)t.plane * 3 * band : nullptr;
+        // coefficient rows / columns feeding the valid outputs of an edge tile: a <= a_max -> k_local <= a_max/2 + H2-1
+        const int amax_h = min(TH - 1, lv.offH + lv.out_h - 1 - aH);
+        const int amax_w = min(TW - 1, lv.offW + lv.out_w - 1 - aW);
+        const int nrows = min(KH, amax_h / 2 + H2);
+        const int ncols = min(KWP, amax_w / 2 + H2);
+        // kW0 is even whenever in_vec2 is set (checked on the host)
+        if (lv.in_vec2)
+            stage_synthesis<2, KH, KWP, NT>(sub_s, lowp, lv.low_rs, hip, band, kH0, kW0, lv.h, lv.w, p.periodic, nrows, ncols, tid);
+        else
+            stage_synthesis<1, KH, KWP, NT>(sub_s, lowp, lv.low_rs, hip, band, kH0, kW0, lv.h, lv.w, p.periodic, nrows, ncols, tid);
+    }
 
-    const int tid = threadIdx.x;
-    TileIter it, nx;
-    it.init(p.sched);
-    nx = it;
-    sfb_issue<L, TW, TH, NT>(smem_s, p, it, tid);
-    cp_async_commit();
-
-    for (int buf = 0; it.tile < p.sched.total; buf ^= 1, it = nx) {
-        const float* sub = smem + buf * (4 * PB);  // [4][KH][KWP]  LL, LH, HL, HH
-        nx.next(p.sched);
-        if (nx.tile < p.sched.total) sfb_issue<L, TW, TH, NT>(smem_s + (unsigned)((buf ^ 1) * (4 * PB * 4)), p, nx, tid);
-        cp_async_commit();
-        cp_async_wait<1>();
-        __syncthreads();
-
-        // ---- W synthesis: each item makes four consecutive outputs (a = 4qq .. 4qq+3) of one coefficient row,
-        //      for both the h_lo branch (LL, HL) and the h_hi branch (LH, HH)
-        {
-            const int qq = tid % NQ;
-            int r = tid / NQ;
-            const float* s0 = sub + r * KWP + 2 * qq;
-            float* d = u_lo + r * TW + 4 * qq;
-            for (; r < KH; r += QSTEP, s0 += QSTEP * KWP, d += QSTEP * TW) {
-                float c[4][2 * NV2];  // local coefficients 2qq .. 2qq+2NV2-1 of LL, LH, HL, HH
+    // W synthesis: each item makes four consecutive outputs (a = 4qq .. 4qq+3) of one coefficient row, for both
+    // the h_lo branch (LL, HL) and the h_hi branch (LH, HH)
+    static __device__ __forceinline__ void pass1(const SfbParams& p, const TileRef&, const float* sub, float* u, int tid) {
+        const int qq = tid % NQ;
+        int r = tid / NQ;
+        const float* s0 = sub + r * KWP + 2 * qq;
+        float* d = u + r * TW + 4 * qq;
+        for (; r < KH; r += QSTEP, s0 += QSTEP * KWP, d += QSTEP * TW) {
+            float c[4][2 * NV2];  // local coefficients 2qq .. 2qq+2NV2-1 of LL, LH, HL, HH
 #pragma unroll
-                for (int b = 0; b < 4; ++b)
+            for (int b = 0; b < 4; ++b)
 #pragma unroll
-                    for (int q = 0; q < NV2; ++q) {
-                        const float2 t = reinterpret_cast<const float2*>(s0 + b * PB)[q];
-                        c[b][2 * q] = t.x;
-                        c[b][2 * q + 1] = t.y;
-                    }
-                float lo[4], hi[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int qo = e >> 1, par = e & 1;  // output a = 2(2qq+qo) + par uses k_local = qo + H2-1-u
-                    float a = 0.f, b = 0.f;
-#pragma unroll
-                    for (int u = 0; u < H2; ++u) {
-                        const int k = qo + H2 - 1 - u;
-                        a = fmaf(c[0][k], p.t.w_lo[par + 2 * u], a);
-                        a = fmaf(c[2][k], p.t.w_hi[par + 2 * u], a);
-                        b = fmaf(c[1][k], p.t.w_lo[par + 2 * u], b);
-                        b = fmaf(c[3][k], p.t.w_hi[par + 2 * u], b);
-                    }
-                    lo[e] = a;
-                    hi[e] = b;
+                for (int q = 0; q < NV2; ++q) {
+                    const float2 t = reinterpret_cast<const float2*>(s0 + b * PB)[q];
+                    c[b][2 * q] = t.x;
+                    c[b][2 * q + 1] = t.y;
                 }
-                *reinterpret_cast<float4*>(d) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                *reinterpret_cast<float4*>(d + KH * TW) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            float lo[4], hi[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int qo = e >> 1, par = e & 1;  // output a = 2(2qq+qo) + par uses k_local = qo + H2-1-u
+                float a = 0.f, b = 0.f;
+#pragma unroll
+                for (int uu = 0; uu < H2; ++uu) {
+                    const int k = qo + H2 - 1 - uu;
+                    a = fmaf(c[0][k], p.t.w_lo[par + 2 * uu], a);
+                    a = fmaf(c[2][k], p.t.w_hi[par + 2 * uu], a);
+                    b = fmaf(c[1][k], p.t.w_lo[par + 2 * uu], b);
+                    b = fmaf(c[3][k], p.t.w_hi[par + 2 * uu], b);
+                }
+                lo[e] = a;
+                hi[e] = b;
             }
+            *reinterpret_cast<float4*>(d) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<float4*>(d + KH * TW) = make_float4(hi[0], hi[1], hi[2], hi[3]);
         }
-        __syncthreads();
+    }
 
-        // ---- H synthesis: thread = two adjacent output columns, RS consecutive output rows
-        {
-            const int cp = tid % CP;
-            const int s = tid / CP;
-            float2 vlo[NR], vhi[NR];
-            const float2* plo = reinterpret_cast<const float2*>(u_lo + (s * (RS / 2)) * TW + 2 * cp);
-            const float2* phi = reinterpret_cast<const float2*>(u_hi + (s * (RS / 2)) * TW + 2 * cp);
+    // H synthesis: thread = two adjacent output columns, RS consecutive output rows
+    static __device__ __forceinline__ void pass2(const SfbParams& p, const TileRef& t, const float* u, int tid) {
+        const SfbLevel& lv = p.lv[t.level];
+        const int cp = tid % CP;
+        const int s = tid / CP;
+        float2 vlo[NR], vhi[NR];
+        const float2* plo = reinterpret_cast<const float2*>(u + (s * (RS / 2)) * TW + 2 * cp);
+        const float2* phi = reinterpret_cast<const float2*>(u + KH * TW + (s * (RS / 2)) * TW + 2 * cp);
 #pragma unroll
-            for (int r = 0; r < NR; ++r) {
-                vlo[r] = plo[r * (TW / 2)];
-                vhi[r] = phi[r * (TW / 2)];
+        for (int r = 0; r < NR; ++r) {
+            vlo[r] = plo[r * (TW / 2)];
+            vhi[r] = phi[r * (TW / 2)];
+        }
+        float2 y[RS];
+#pragma unroll
+        for (int i = 0; i < RS / 2; ++i) {
+            float2 ye = make_float2(0.f, 0.f), yo = ye;
+#pragma unroll
+            for (int uu = 0; uu < H2; ++uu) {
+                const int r = i - uu + H2 - 1;  // local coefficient row
+                const float a0 = p.t.h_lo[2 * uu], b0 = p.t.h_hi[2 * uu], a1 = p.t.h_lo[2 * uu + 1], b1 = p.t.h_hi[2 * uu + 1];
+                ye.x = fmaf(vlo[r].x, a0, ye.x); ye.y = fmaf(vlo[r].y, a0, ye.y);
+                ye.x = fmaf(vhi[r].x, b0, ye.x); ye.y = fmaf(vhi[r].y, b0, ye.y);
+                yo.x = fmaf(vlo[r].x, a1, yo.x); yo.y = fmaf(vlo[r].y, a1, yo.y);
+                yo.x = fmaf(vhi[r].x, b1, yo.x); yo.y = fmaf(vhi[r].y, b1, yo.y);
             }
-            float2 y[RS];
+            y[2 * i] = ye;
+            y[2 * i + 1] = yo;
+        }
+        const int out_h = lv.out_h, out_w = lv.out_w;
+        const int nW = lv.a0W + t.tw * TW + 2 * cp - lv.offW;
+        const int nH = lv.a0H + t.th * TH + s * RS - lv.offH;
+        float* q = lv.y + ((long long)t.plane * out_h + nH) * out_w + nW;  // only dereferenced where valid
+        if (lv.out_vec2 && nH >= 0 && nH + RS <= out_h && nW >= 0 && nW + 1 < out_w) {
 #pragma unroll
-            for (int i = 0; i < RS / 2; ++i) {
-                float2 ye = make_float2(0.f, 0.f), yo = ye;
-#pragma unroll
-                for (int u = 0; u < H2; ++u) {
-                    const int r = i - u + H2 - 1;  // local coefficient row
-                    const float a0 = p.t.h_lo[2 * u], b0 = p.t.h_hi[2 * u], a1 = p.t.h_lo[2 * u + 1], b1 = p.t.h_hi[2 * u + 1];
-                    ye.x = fmaf(vlo[r].x, a0, ye.x); ye.y = fmaf(vlo[r].y, a0, ye.y);
-                    ye.x = fmaf(vhi[r].x, b0, ye.x); ye.y = fmaf(vhi[r].y, b0, ye.y);
-                    yo.x = fmaf(vlo[r].x, a1, yo.x); yo.y = fmaf(vlo[r].y, a1, yo.y);
-                    yo.x = fmaf(vhi[r].x, b1, yo.x); yo.y = fmaf(vhi[r].y, b1, yo.y);
-                }
-                y[2 * i] = ye;
-                y[2 * i + 1] = yo;
+            for (int i = 0; i < RS; ++i) {
+                *reinterpret_cast<float2*>(q) = y[i];
+                q += out_w;
             }
-            const int nW = p.a0W + it.tw * TW + 2 * cp - p.offW;
-            const int nH = p.a0H + it.th * TH + s * RS - p.offH;
-            float* q = p.y + ((size_t)it.plane * p.out_h + nH) * p.out_w + nW;  // only dereferenced where valid
-            if (p.out_vec2 && nH >= 0 && nH + RS <= p.out_h && nW >= 0 && nW + 1 < p.out_w) {
+        } else {
+            const bool ok0 = nW >= 0 && nW < out_w;
+            const bool ok1 = nW + 1 >= 0 && nW + 1 < out_w;
 #pragma unroll
-                for (int i = 0; i < RS; ++i) {
-                    *reinterpret_cast<float2*>(q) = y[i];
-                    q += p.out_w;
+            for (int i = 0; i < RS; ++i) {
+                const int row = nH + i;
+                if (row >= 0 && row < out_h) {
+                    if (ok0) q[0] = y[i].x;
+                    if (ok1) q[1] = y[i].y;
                 }
-            } else {
-                const bool ok0 = nW >= 0 && nW < p.out_w;
-                const bool ok1 = nW + 1 >= 0 && nW + 1 < p.out_w;
-#pragma unroll
-                for (int i = 0; i < RS; ++i) {
-                    const int row = nH + i;
-                    if (row >= 0 && row < p.out_h) {
-                        if (ok0) q[0] = y[i].x;
-                        if (ok1) q[1] = y[i].y;
-                    }
-                    q += p.out_w;
-                }
+                q += out_w;
             }
         }
     }
-}
+};
 
-// synthesis, direct: one thread per output sample; any tap count.
-__global__ void __launch_bounds__(kThreads) sfb2d_direct_kernel(const __grid_constant__ SfbParams p) {
-    const size_t total = (size_t)p.planes * p.out_h * p.out_w;
-    const size_t band = (size_t)p.h * p.w;
+// synthesis, direct: one thread per output sample of ONE level; any tap count.
+struct SfbDirectParams {
+    SfbLevel lv;
+    int planes, periodic, Lw, Lh;
+    Taps t;
+};
+
+__global__ void __launch_bounds__(kThreads) sfb2d_direct_kernel(const __grid_constant__ SfbDirectParams p) {
+    const SfbLevel& lv = p.lv;
+    const size_t total = (size_t)p.planes * lv.out_h * lv.out_w;
+    const size_t band = (size_t)lv.h * lv.w;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x) {
-        const int nW = (int)(idx % p.out_w);
-        const int nH = (int)((idx / p.out_w) % p.out_h);
-        const int plane = (int)(idx / ((size_t)p.out_h * p.out_w));
-        const float* __restrict__ lowp = p.low + (long long)plane * p.low_ps;
-        const float* __restrict__ hip = p.highs ? p.highs + (size_t)plane * 3 * band : nullptr;
-        const int AH = nH + p.offH, AW = nW + p.offW;
+        const int nW = (int)(idx % lv.out_w);
+        const int nH = (int)((idx / lv.out_w) % lv.out_h);
+        const int plane = (int)(idx / ((size_t)lv.out_h * lv.out_w));
+        const float* __restrict__ lowp = lv.low + (long long)plane * lv.low_ps;
+        const float* __restrict__ hip = lv.highs ? lv.highs + (size_t)plane * 3 * band : nullptr;
+        const int AH = nH + lv.offH, AW = nW + lv.offW;
         float y = 0.f;
         for (int tH = AH & 1; tH < p.Lh; tH += 2) {
-            const int kr = coef_index((AH - tH) / 2, p.h, p.periodic);
+            const int kr = coef_index((AH - tH) / 2, lv.h, p.periodic);
             if (kr < 0) continue;
             float lo = 0.f, hi = 0.f;  // W-synthesised values to be combined with h_lo / h_hi
             for (int tW = AW & 1; tW < p.Lw; tW += 2) {
-                const int kc = coef_index((AW - tW) / 2, p.w, p.periodic);
+                const int kc = coef_index((AW - tW) / 2, lv.w, p.periodic);
                 if (kc < 0) continue;
-                const float ll = __ldg(lowp + (long long)kr * p.low_rs + kc);
+                const float ll = __ldg(lowp + (long long)kr * lv.low_rs + kc);
                 lo = fmaf(ll, p.t.w_lo[tW], lo);
                 if (hip) {
-                    const float* q = hip + (size_t)kr * p.w + kc;
+                    const float* q = hip + (size_t)kr * lv.w + kc;
                     hi = fmaf(__ldg(q), p.t.w_lo[tW], hi);               // LH
                     lo = fmaf(__ldg(q + band), p.t.w_hi[tW], lo);        // HL
                     hi = fmaf(__ldg(q + 2 * band), p.t.w_hi[tW], hi);    // HH
@@ -572,7 +674,7 @@ __global__ void __launch_bounds__(kThreads) sfb2d_direct_kernel(const __grid_con
             y = fmaf(lo, p.t.h_lo[tH], y);
             y = fmaf(hi, p.t.h_hi[tH], y);
         }
-        p.y[idx] = y;
+        lv.y[idx] = y;
     }
 }
 
@@ -607,6 +709,7 @@ static int fill_taps(Taps& t, const float* w_lo, const float* w_hi, int Lw, cons
 }
 
 static int coeff_len(int n, int l, int mode) { return mode == B200W_MODE_PERIODIZATION ? (n + 1) / 2 : (n + l - 1) / 2; }
+static int idwt_len(int m, int l, int mode) { return mode == B200W_MODE_PERIODIZATION ? 2 * m : 2 * m - l + 2; }
 
 // left padding of the analysis bank along one axis; also validates the axis
 static int analysis_offset(int n, int l, int mode, int* off) {
@@ -623,6 +726,7 @@ static int analysis_offset(int n, int l, int mode, int* off) {
 }
 
 static bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+static int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 constexpr int kMaxDevices = 64;
 
@@ -647,84 +751,255 @@ static DeviceInfo device_info() {
     return d;
 }
 
-// Persistent launch: one CTA per resident slot (SMs x occupancy), each looping over tiles.
-// `occ` is the caller's per-kernel, per-device cache of the occupancy (0 = not yet queried); the query also
-// raises the kernel's dynamic shared memory limit once.  Function attributes and occupancy are immutable
-// facts about (kernel, device), so caching them keeps the library re-entrant.
-template <typename K, typename P>
-static int launch_tiles(K kernel, P& p, int tiles_w, int tiles_h, int threads, size_t smem, int* occ_cache,
-                        cudaStream_t st) {
+// Persistent launch: grid = min(tiles, SMs x occupancy).  A multi-level chain spins on completion counters, so
+// its CTAs must all be resident: it is launched cooperatively (the runtime refuses the launch otherwise) and
+// the counters are cleared on the stream first.  `occ_cache` is the caller's per-kernel, per-device cache of
+// the occupancy (0 = not queried yet; the query also raises the kernel's dynamic shared-memory limit).  Both are
+// immutable facts about (kernel, device), so caching them keeps the library re-entrant.
+template <class Op>
+static int launch_chain(typename Op::Params& p, int* occ_cache, cudaStream_t st) {
+    auto kernel = chain_kernel<Op>;
     const DeviceInfo di = device_info();
     int& occ = occ_cache[di.dev];
     if (occ == 0) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Op::smem);
         if (e != cudaSuccess) return set_last_cuda_error(e);
         int o = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kernel, threads, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kernel, Op::NT, Op::smem);
         if (e != cudaSuccess) return set_last_cuda_error(e);
         occ = o > 0 ? o : 1;
     }
-    const long long total = (long long)tiles_w * tiles_h * p.planes;
     long long grid = (long long)di.sms * occ;
-    if (grid > total) grid = total;
-    p.sched.total = total;
-    p.sched.tiles_w = tiles_w;
-    p.sched.tiles_h = tiles_h;
-    p.sched.d_w = (int)(grid % tiles_w);
-    p.sched.d_h = (int)((grid / tiles_w) % tiles_h);
-    p.sched.d_p = (int)(grid / ((long long)tiles_w * tiles_h));
-    kernel<<<(unsigned)grid, threads, smem, st>>>(p);
-    cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? B200W_OK : set_last_cuda_error(e);
-}
-
-template <typename K, typename P>
-static int launch_flat(K kernel, const P& p, size_t grid, cudaStream_t st) {
-    kernel<<<(unsigned)grid, kThreads, 0, st>>>(p);
-    cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? B200W_OK : set_last_cuda_error(e);
-}
-
-static int ceil_div(int a, int b) { return (a + b - 1) / b; }
-
-template <int L>
-static int launch_afb_tiled(AfbParams& p, cudaStream_t st) {
-    // two tile shapes: 32x32 outputs / 128 threads, or 64 wide x 32 / 256 threads (less halo); take the wide
-    // one unless it wastes noticeably more of the padded output area
-    const long long a32 = (long long)ceil_div(p.Wo, 32) * 32;
-    const long long a64 = (long long)ceil_div(p.Wo, 64) * 64;
-    if (p.Wo >= 128 && a64 * 100 <= a32 * 103) {
-        constexpr int TW = 64, TH = 32, NT = 256;
-        static int occ[kMaxDevices] = {0};
-        return launch_tiles(afb2d_tile_kernel<L, TW, TH, NT>, p, ceil_div(p.Wo, TW), ceil_div(p.Ho, TH), NT,
-                            AfbCfg<L, TW, TH, NT>::smem, occ, st);
+    if (grid > p.total) grid = p.total;
+    cudaError_t e;
+    if (p.J > 1) {
+        e = cudaMemsetAsync(p.done, 0, sizeof(unsigned) * (size_t)p.J * p.planes, st);
+        if (e != cudaSuccess) return set_last_cuda_error(e);
+        void* args[] = {(void*)&p};
+        e = cudaLaunchCooperativeKernel((const void*)kernel, dim3((unsigned)grid), dim3(Op::NT), args, Op::smem, st);
+    } else {
+        kernel<<<(unsigned)grid, Op::NT, Op::smem, st>>>(p);
+        e = cudaGetLastError();
     }
-    constexpr int TW = 32, TH = 32, NT = 128;
-    static int occ[kMaxDevices] = {0};
-    return launch_tiles(afb2d_tile_kernel<L, TW, TH, NT>, p, ceil_div(p.Wo, TW), ceil_div(p.Ho, TH), NT,
-                        AfbCfg<L, TW, TH, NT>::smem, occ, st);
+    return e == cudaSuccess ? B200W_OK : set_last_cuda_error(e);
+}
+
+template <int TW, int TH>
+static void afb_layout(AfbParams& p) {
+    long long base = 0;
+    for (int j = 0; j < p.J; ++j) {
+        p.lv[j].tiles_w = ceil_div(p.lv[j].Wo, TW);
+        p.lv[j].tiles_h = ceil_div(p.lv[j].Ho, TH);
+        p.lv[j].tile_base = base;
+        base += (long long)p.lv[j].tiles_w * p.lv[j].tiles_h * p.planes;
+    }
+    p.total = base;
 }
 
 template <int L>
-static int launch_sfb_tiled(SfbParams& p, cudaStream_t st) {
-    constexpr int TW = 64, TH = 64, NT = 256;
+static int launch_afb_chain(AfbParams& p, cudaStream_t st) {
+    // two tile shapes: 32x32 outputs / 128 threads, or 64 wide x 32 / 256 threads (less halo); take the wide
+    // one for wide single-level problems unless it wastes noticeably more of the padded output area
+    const int Wo = p.lv[0].Wo;
+    const long long a32 = (long long)ceil_div(Wo, 32) * 32;
+    const long long a64 = (long long)ceil_div(Wo, 64) * 64;
+    if (p.J == 1 && Wo >= 128 && a64 * 100 <= a32 * 103) {
+        using Op = AfbOp<L, 64, 32, 256>;
+        static int occ[kMaxDevices] = {0};
+        afb_layout<Op::TW, Op::TH>(p);
+        return launch_chain<Op>(p, occ, st);
+    }
+    using Op = AfbOp<L, 32, 32, 128>;
     static int occ[kMaxDevices] = {0};
-    p.a0W = p.offW & ~1;
-    p.a0H = p.offH & ~1;
-    const int tiles_w = ceil_div(p.offW + p.out_w - p.a0W, TW);
-    const int tiles_h = ceil_div(p.offH + p.out_h - p.a0H, TH);
-    // tile 0 starts at coefficient column a0W/2 - (L/2-1): even for every non-periodization mode
-    const int kW0 = p.a0W / 2 - (L / 2 - 1);
-    if ((kW0 & 1) != 0) p.in_vec2 = 0;
-    if ((p.offW & 1) != 0) p.out_vec2 = 0;
-    return launch_tiles(sfb2d_tile_kernel<L, TW, TH, NT>, p, tiles_w, tiles_h, NT, SfbCfg<L, TW, TH, NT>::smem, occ,
-                        st);
+    afb_layout<Op::TW, Op::TH>(p);
+    return launch_chain<Op>(p, occ, st);
+}
+
+template <int L>
+static int launch_sfb_chain(SfbParams& p, cudaStream_t st) {
+    using Op = SfbOp<L, 64, 64, 256>;
+    static int occ[kMaxDevices] = {0};
+    long long base = 0;
+    for (int j = 0; j < p.J; ++j) {
+        SfbLevel& lv = p.lv[j];
+        lv.a0W = lv.offW & ~1;
+        lv.a0H = lv.offH & ~1;
+        lv.tiles_w = ceil_div(lv.offW + lv.out_w - lv.a0W, Op::TW);
+        lv.tiles_h = ceil_div(lv.offH + lv.out_h - lv.a0H, Op::TH);
+        // tile 0 starts at coefficient column a0W/2 - (L/2-1): even for every non-periodization mode
+        const int kW0 = lv.a0W / 2 - (L / 2 - 1);
+        if ((kW0 & 1) != 0) lv.in_vec2 = 0;
+        if ((lv.offW & 1) != 0) lv.out_vec2 = 0;
+        lv.tile_base = base;
+        base += (long long)lv.tiles_w * lv.tiles_h * p.planes;
+    }
+    p.total = base;
+    return launch_chain<Op>(p, occ, st);
 }
 
 static size_t direct_grid(size_t total) {
     size_t g = (total + kThreads - 1) / kThreads;
     const size_t cap = 148 * 16;
     return g < 1 ? 1 : (g > cap ? cap : g);
+}
+
+static int tiled_supported(int Lw, int Lh) {
+    return Lw == Lh && (Lw % 2) == 0 && Lw >= 2 && Lw <= 16 && !force_direct();
+}
+
+// ---- analysis chain --------------------------------------------------------------------------------
+static int run_afb_chain(const float* x, int64_t x_ps, int64_t x_rs, int planes, int H, int W, const float* w_lo,
+                         const float* w_hi, int Lw, const float* h_lo, const float* h_hi, int Lh, int mode, int J,
+                         const int* pad_hw, float* const* low, float* const* highs, void* workspace,
+                         size_t workspace_bytes, cudaStream_t st) {
+    if (!mode_supported(mode)) return B200W_ERR_BAD_MODE;
+    if (J < 1 || J > kMaxLevels) return B200W_ERR_BAD_SHAPE;
+    if (!x || !low || !highs) return B200W_ERR_NULL_POINTER;
+    if (planes < 1 || H < 1 || W < 1) return B200W_ERR_BAD_SHAPE;
+    AfbParams p;
+    int rc = fill_taps(p.t, w_lo, w_hi, Lw, h_lo, h_hi, Lh);
+    if (rc) return rc;
+    p.J = J;
+    p.planes = planes;
+    p.mode = mode;
+    p.done = nullptr;
+    int h = H, w = W;  // real size of the level input
+    for (int j = 0; j < J; ++j) {
+        AfbLevel& lv = p.lv[j];
+        if (!low[j] || !highs[j]) return B200W_ERR_NULL_POINTER;
+        const int ph = (pad_hw && j > 0) ? pad_hw[2 * j] : 0, pw = (pad_hw && j > 0) ? pad_hw[2 * j + 1] : 0;
+        if (ph < 0 || ph > 1 || pw < 0 || pw > 1) return B200W_ERR_BAD_SHAPE;
+        lv.x = j == 0 ? x : low[j - 1];
+        lv.x_ps = j == 0 ? x_ps : (long long)h * w;
+        lv.x_rs = j == 0 ? x_rs : w;
+        lv.Hreal = h;
+        lv.Wreal = w;
+        lv.H = h + ph;
+        lv.W = w + pw;
+        if ((rc = analysis_offset(lv.W, Lw, mode, &lv.offW))) return rc;
+        if ((rc = analysis_offset(lv.H, Lh, mode, &lv.offH))) return rc;
+        lv.Ho = coeff_len(lv.H, Lh, mode);
+        lv.Wo = coeff_len(lv.W, Lw, mode);
+        lv.low = low[j];
+        lv.highs = highs[j];
+        // staging vector width: the first staged column of every tile is 2*TW*tw - offW
+        lv.in_vec = 1;
+        if ((lv.offW % 2) == 0 && (lv.x_rs % 2) == 0 && (lv.x_ps % 2) == 0 && aligned_to(lv.x, 8)) lv.in_vec = 2;
+        if (lv.in_vec == 2 && (lv.offW % 4) == 0 && (lv.x_rs % 4) == 0 && (lv.x_ps % 4) == 0 && aligned_to(lv.x, 16))
+            lv.in_vec = 4;
+        lv.out_vec2 = ((lv.Wo % 2) == 0 && aligned_to(lv.low, 8) && aligned_to(lv.highs, 8)) ? 1 : 0;
+        h = lv.Ho;
+        w = lv.Wo;
+    }
+    if (tiled_supported(Lw, Lh)) {
+        if (J > 1) {
+            if (!workspace || workspace_bytes < sizeof(unsigned) * (size_t)J * planes) return B200W_ERR_WORKSPACE;
+            p.done = (unsigned*)workspace;
+        }
+        switch (Lw) {
+            case 2: return launch_afb_chain<2>(p, st);
+            case 4: return launch_afb_chain<4>(p, st);
+            case 6: return launch_afb_chain<6>(p, st);
+            case 8: return launch_afb_chain<8>(p, st);
+            case 10: return launch_afb_chain<10>(p, st);
+            case 12: return launch_afb_chain<12>(p, st);
+            case 14: return launch_afb_chain<14>(p, st);
+            default: return launch_afb_chain<16>(p, st);
+        }
+    }
+    for (int j = 0; j < J; ++j) {  // level by level with the direct kernel
+        AfbDirectParams d;
+        d.lv = p.lv[j];
+        d.planes = planes;
+        d.mode = mode;
+        d.Lw = Lw;
+        d.Lh = Lh;
+        d.t = p.t;
+        afb2d_direct_kernel<<<(unsigned)direct_grid((size_t)planes * d.lv.Ho * d.lv.Wo), kThreads, 0, st>>>(d);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return set_last_cuda_error(e);
+    }
+    return B200W_OK;
+}
+
+// ---- synthesis chain -------------------------------------------------------------------------------
+// levels are given finest first (index j like yh[j]); the chain runs j = J-1 .. 0
+static int run_sfb_chain(const float* yl, int64_t yl_ps, int64_t yl_rs, const float* const* highs, int planes,
+                         const int* hs, const int* ws, const float* w_lo, const float* w_hi, int Lw, const float* h_lo,
+                         const float* h_hi, int Lh, int mode, int J, const int* out_hs, const int* out_ws,
+                         float* const* y, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    if (!mode_supported(mode)) return B200W_ERR_BAD_MODE;
+    if (J < 1 || J > kMaxLevels) return B200W_ERR_BAD_SHAPE;
+    if (!yl || !y || !hs || !ws || !out_hs || !out_ws) return B200W_ERR_NULL_POINTER;
+    if (planes < 1) return B200W_ERR_BAD_SHAPE;
+    SfbParams p;
+    int rc = fill_taps(p.t, w_lo, w_hi, Lw, h_lo, h_hi, Lh);
+    if (rc) return rc;
+    const bool per = mode == B200W_MODE_PERIODIZATION;
+    p.J = J;
+    p.planes = planes;
+    p.periodic = per ? 1 : 0;
+    p.done = nullptr;
+    for (int c = 0; c < J; ++c) {  // chain position c handles level j = J-1-c
+        const int j = J - 1 - c;
+        SfbLevel& lv = p.lv[c];
+        const int h = hs[j], w = ws[j];
+        if (h < 1 || w < 1 || out_hs[j] < 1 || out_ws[j] < 1) return B200W_ERR_BAD_SHAPE;
+        if (!y[j]) return B200W_ERR_NULL_POINTER;
+        if (per && (2 * h < Lh || 2 * w < Lw)) return B200W_ERR_PER_TOO_SHORT;
+        if (out_hs[j] > idwt_len(h, Lh, mode) || out_ws[j] > idwt_len(w, Lw, mode)) return B200W_ERR_BAD_SHAPE;
+        if (c == 0) {
+            lv.low = yl;
+            lv.low_ps = yl_ps;
+            lv.low_rs = yl_rs;
+        } else {  // the previous chain output, of which the top-left h x w block is used ('unpad')
+            if (out_hs[j + 1] < h || out_ws[j + 1] < w) return B200W_ERR_BAD_SHAPE;
+            lv.low = y[j + 1];
+            lv.low_ps = (long long)out_hs[j + 1] * out_ws[j + 1];
+            lv.low_rs = out_ws[j + 1];
+        }
+        lv.highs = highs ? highs[j] : nullptr;
+        lv.y = y[j];
+        lv.h = h;
+        lv.w = w;
+        lv.out_h = out_hs[j];
+        lv.out_w = out_ws[j];
+        lv.offW = per ? Lw / 2 - 1 : Lw - 2;
+        lv.offH = per ? Lh / 2 - 1 : Lh - 2;
+        lv.a0W = lv.a0H = 0;
+        lv.in_vec2 = ((w % 2) == 0 && (lv.low_rs % 2) == 0 && (lv.low_ps % 2) == 0 && aligned_to(lv.low, 8) &&
+                      (!lv.highs || aligned_to(lv.highs, 8))) ? 1 : 0;
+        lv.out_vec2 = ((lv.out_w % 2) == 0 && aligned_to(lv.y, 8)) ? 1 : 0;
+    }
+    if (tiled_supported(Lw, Lh)) {
+        if (J > 1) {
+            if (!workspace || workspace_bytes < sizeof(unsigned) * (size_t)J * planes) return B200W_ERR_WORKSPACE;
+            p.done = (unsigned*)workspace;
+        }
+        switch (Lw) {
+            case 2: return launch_sfb_chain<2>(p, st);
+            case 4: return launch_sfb_chain<4>(p, st);
+            case 6: return launch_sfb_chain<6>(p, st);
+            case 8: return launch_sfb_chain<8>(p, st);
+            case 10: return launch_sfb_chain<10>(p, st);
+            case 12: return launch_sfb_chain<12>(p, st);
+            case 14: return launch_sfb_chain<14>(p, st);
+            default: return launch_sfb_chain<16>(p, st);
+        }
+    }
+    for (int c = 0; c < J; ++c) {
+        SfbDirectParams d;
+        d.lv = p.lv[c];
+        d.planes = planes;
+        d.periodic = p.periodic;
+        d.Lw = Lw;
+        d.Lh = Lh;
+        d.t = p.t;
+        sfb2d_direct_kernel<<<(unsigned)direct_grid((size_t)planes * d.lv.out_h * d.lv.out_w), kThreads, 0, st>>>(d);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return set_last_cuda_error(e);
+    }
+    return B200W_OK;
 }
 
 }  // namespace b200w
@@ -740,55 +1015,31 @@ extern "C" int b200w_dwt_coeff_len(int n, int l, int mode) {
 extern "C" int b200w_idwt_len(int m, int l, int mode) {
     if (!mode_supported(mode)) return B200W_ERR_BAD_MODE;
     if (m < 1 || l < 1) return B200W_ERR_BAD_SHAPE;
-    return mode == B200W_MODE_PERIODIZATION ? 2 * m : 2 * m - l + 2;
+    return idwt_len(m, l, mode);
+}
+
+extern "C" size_t b200w_dwt2_workspace_bytes(int planes, int J) {
+    if (planes < 1 || J < 1) return 0;
+    return sizeof(unsigned) * (size_t)planes * (size_t)J;
 }
 
 extern "C" int b200w_afb2d_f32(const float* x, int64_t x_plane_stride, int64_t x_row_stride, int planes, int H,
                                int W, const float* w_lo, const float* w_hi, int Lw, const float* h_lo,
                                const float* h_hi, int Lh, int mode, float* low, float* highs, void* stream) {
     if (!mode_supported(mode)) return B200W_ERR_BAD_MODE;
-    if (!x || !low || !highs) return B200W_ERR_NULL_POINTER;
-    if (planes < 1 || H < 1 || W < 1) return B200W_ERR_BAD_SHAPE;
-    AfbParams p;
-    int rc = fill_taps(p.t, w_lo, w_hi, Lw, h_lo, h_hi, Lh);
-    if (rc) return rc;
-    if ((rc = analysis_offset(W, Lw, mode, &p.offW))) return rc;
-    if ((rc = analysis_offset(H, Lh, mode, &p.offH))) return rc;
-    p.x = x;
-    p.low = low;
-    p.highs = highs;
-    p.x_ps = x_plane_stride;
-    p.x_rs = x_row_stride;
-    p.planes = planes;
-    p.H = H;
-    p.W = W;
-    p.Ho = coeff_len(H, Lh, mode);
-    p.Wo = coeff_len(W, Lw, mode);
-    p.mode = mode;
-    p.Lw = Lw;
-    p.Lh = Lh;
-    // staging vector width: the first staged column of every tile is 2*TW*tw - offW
-    p.in_vec = 1;
-    if ((p.offW % 2) == 0 && (x_row_stride % 2) == 0 && (x_plane_stride % 2) == 0 && aligned_to(x, 8)) p.in_vec = 2;
-    if (p.in_vec == 2 && (p.offW % 4) == 0 && (x_row_stride % 4) == 0 && (x_plane_stride % 4) == 0 && aligned_to(x, 16))
-        p.in_vec = 4;
-    p.out_vec2 = ((p.Wo % 2) == 0 && aligned_to(low, 8) && aligned_to(highs, 8)) ? 1 : 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (Lw == Lh && !force_direct()) {
-        switch (Lw) {
-            case 2: return launch_afb_tiled<2>(p, st);
-            case 4: return launch_afb_tiled<4>(p, st);
-            case 6: return launch_afb_tiled<6>(p, st);
-            case 8: return launch_afb_tiled<8>(p, st);
-            case 10: return launch_afb_tiled<10>(p, st);
-            case 12: return launch_afb_tiled<12>(p, st);
-            case 14: return launch_afb_tiled<14>(p, st);
-            case 16: return launch_afb_tiled<16>(p, st);
-            default: break;
-        }
-    }
-    const size_t total = (size_t)planes * p.Ho * p.Wo;
-    return launch_flat(afb2d_direct_kernel, p, direct_grid(total), st);
+    if (!low || !highs) return B200W_ERR_NULL_POINTER;
+    float* lows[1] = {low};
+    float* his[1] = {highs};
+    return run_afb_chain(x, x_plane_stride, x_row_stride, planes, H, W, w_lo, w_hi, Lw, h_lo, h_hi, Lh, mode, 1,
+                         nullptr, lows, his, nullptr, 0, (cudaStream_t)stream);
+}
+
+extern "C" int b200w_dwt2_f32(const float* x, int64_t x_plane_stride, int64_t x_row_stride, int planes, int H, int W,
+                              const float* w_lo, const float* w_hi, int Lw, const float* h_lo, const float* h_hi,
+                              int Lh, int mode, int J, const int* pad_hw, float* const* low, float* const* highs,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+    return run_afb_chain(x, x_plane_stride, x_row_stride, planes, H, W, w_lo, w_hi, Lw, h_lo, h_hi, Lh, mode, J,
+                         pad_hw, low, highs, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int b200w_sfb2d_f32(const float* low, int64_t low_plane_stride, int64_t low_row_stride,
@@ -798,47 +1049,17 @@ extern "C" int b200w_sfb2d_f32(const float* low, int64_t low_plane_stride, int64
     if (!mode_supported(mode)) return B200W_ERR_BAD_MODE;
     if (!low || !y) return B200W_ERR_NULL_POINTER;
     if (planes < 1 || h < 1 || w < 1 || out_h < 1 || out_w < 1) return B200W_ERR_BAD_SHAPE;
-    SfbParams p;
-    int rc = fill_taps(p.t, w_lo, w_hi, Lw, h_lo, h_hi, Lh);
-    if (rc) return rc;
-    const bool per = mode == B200W_MODE_PERIODIZATION;
-    if (per && (2 * h < Lh || 2 * w < Lw)) return B200W_ERR_PER_TOO_SHORT;
-    const int full_h = per ? 2 * h : 2 * h - Lh + 2;
-    const int full_w = per ? 2 * w : 2 * w - Lw + 2;
-    if (out_h > full_h || out_w > full_w) return B200W_ERR_BAD_SHAPE;
-    p.low = low;
-    p.highs = highs;
-    p.y = y;
-    p.low_ps = low_plane_stride;
-    p.low_rs = low_row_stride;
-    p.planes = planes;
-    p.h = h;
-    p.w = w;
-    p.out_h = out_h;
-    p.out_w = out_w;
-    p.periodic = per ? 1 : 0;
-    p.offW = per ? Lw / 2 - 1 : Lw - 2;
-    p.offH = per ? Lh / 2 - 1 : Lh - 2;
-    p.Lw = Lw;
-    p.Lh = Lh;
-    p.a0W = p.a0H = 0;
-    p.in_vec2 = ((w % 2) == 0 && (low_row_stride % 2) == 0 && (low_plane_stride % 2) == 0 && aligned_to(low, 8) &&
-                 (!highs || aligned_to(highs, 8))) ? 1 : 0;
-    p.out_vec2 = ((out_w % 2) == 0 && aligned_to(y, 8)) ? 1 : 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (Lw == Lh && !force_direct()) {
-        switch (Lw) {
-            case 2: return launch_sfb_tiled<2>(p, st);
-            case 4: return launch_sfb_tiled<4>(p, st);
-            case 6: return launch_sfb_tiled<6>(p, st);
-            case 8: return launch_sfb_tiled<8>(p, st);
-            case 10: return launch_sfb_tiled<10>(p, st);
-            case 12: return launch_sfb_tiled<12>(p, st);
-            case 14: return launch_sfb_tiled<14>(p, st);
-            case 16: return launch_sfb_tiled<16>(p, st);
-            default: break;
-        }
-    }
-    const size_t total = (size_t)planes * out_h * out_w;
-    return launch_flat(sfb2d_direct_kernel, p, direct_grid(total), st);
+    const float* his[1] = {highs};
+    float* ys[1] = {y};
+    return run_sfb_chain(low, low_plane_stride, low_row_stride, his, planes, &h, &w, w_lo, w_hi, Lw, h_lo, h_hi, Lh,
+                         mode, 1, &out_h, &out_w, ys, nullptr, 0, (cudaStream_t)stream);
+}
+
+extern "C" int b200w_idwt2_f32(const float* yl, int64_t yl_plane_stride, int64_t yl_row_stride,
+                               const float* const* highs, int planes, const int* h, const int* w, const float* w_lo,
+                               const float* w_hi, int Lw, const float* h_lo, const float* h_hi, int Lh, int mode,
+                               int J, const int* out_h, const int* out_w, float* const* y, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+    return run_sfb_chain(yl, yl_plane_stride, yl_row_stride, highs, planes, h, w, w_lo, w_hi, Lw, h_lo, h_hi, Lh, mode,
+                         J, out_h, out_w, y, workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -10,6 +10,7 @@ import torch
 import torch.nn as nn
 
 from . import lowlevel
+from .. import ops
 from ..wavelets import as_wavelet, is_wavelet
 
 
@@ -49,13 +50,19 @@ class DWTForward(nn.Module):
         """x: (N, C, H, W) -> (yl, yh); yl (N, C, H', W'), yh[j] (N, C, 3, H'', W'') holding LH, HL, HH,
         finest scale first."""
         mode = lowlevel.mode_to_int(self.mode)
+        lowlevel.int_to_mode(mode)
+        # NB the *_col buffers go into AFB2D's *_row slots at pw/dwt/transform2d.py:70-71: the "col" filters
+        # therefore run along W and the "row" filters along H.  The J-level loop over AFB2D.apply is one launch.
+        taps = [lowlevel.host_taps(f) for f in (self.h0_col, self.h1_col, self.h0_row, self.h1_row)]
         yh = []
         ll = x
-        for _ in range(self.J):
-            # NB the *_col buffers go into AFB2D's *_row slots, exactly as pw/dwt/transform2d.py:70-71
-            # does: the "col" filters therefore run along W and the "row" filters along H.
-            ll, high = lowlevel.AFB2D.apply(ll, self.h0_col, self.h1_col, self.h0_row, self.h1_row, mode)
-            yh.append(high)
+        J = int(self.J)
+        while J > 0:   # chunks of at most MAX_LEVELS levels per launch
+            n = min(J, ops.MAX_LEVELS)
+            outs = ops.DWT2Function.apply(ll, taps[0], taps[1], taps[2], taps[3], mode, n)
+            ll = outs[0]
+            yh.extend(outs[1:])
+            J -= n
         return ll, yh
 
 
@@ -73,14 +80,14 @@ class DWTInverse(nn.Module):
     def forward(self, coeffs):
         yl, yh = coeffs
         mode = lowlevel.mode_to_int(self.mode)
+        lowlevel.int_to_mode(mode)
+        taps = [lowlevel.host_taps(f) for f in (self.g0_col, self.g1_col, self.g0_row, self.g1_row)]
+        yh = list(yh)
         ll = yl
-        for h in yh[::-1]:
-            if h is not None:
-                # 'unpad': a level reconstructed from an odd-sized input is one sample too large
-                # (pw/dwt/transform2d.py:141-145); the crop is a view, the kernel reads it strided
-                if ll.shape[-2] > h.shape[-2]:
-                    ll = ll[..., :-1, :]
-                if ll.shape[-1] > h.shape[-1]:
-                    ll = ll[..., :-1]
-            ll = lowlevel.SFB2D.apply(ll, h, self.g0_col, self.g1_col, self.g0_row, self.g1_row, mode)
+        # the loop over SFB2D.apply incl. the 'unpad' crop (a level reconstructed from an odd-sized input is one
+        # sample too large, pw/dwt/transform2d.py:141-145) is one launch; the crop is a strided read
+        while yh:
+            chunk = yh[-ops.MAX_LEVELS:]
+            yh = yh[:-ops.MAX_LEVELS]
+            ll = ops.IDWT2Function.apply(taps[0], taps[1], taps[2], taps[3], mode, ll, *chunk)
         return ll

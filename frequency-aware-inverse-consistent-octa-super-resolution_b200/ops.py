@@ -26,9 +26,15 @@ _LIB = torch.library.Library("b200wave", "DEF")
 _LIB.define("afb2d(Tensor x, float[] w_lo, float[] w_hi, float[] h_lo, float[] h_hi, int mode) -> (Tensor, Tensor)")
 _LIB.define("sfb2d(Tensor low, Tensor? highs, float[] w_lo, float[] w_hi, float[] h_lo, float[] h_hi, int mode, "
             "int out_h, int out_w) -> Tensor")
+_LIB.define("dwt2(Tensor x, float[] w_lo, float[] w_hi, float[] h_lo, float[] h_hi, int mode, int J, int[] pad_hw) "
+            "-> Tensor[]")
+_LIB.define("idwt2(Tensor yl, Tensor?[] yh, int[] hw, float[] w_lo, float[] w_hi, float[] h_lo, float[] h_hi, int mode, "
+            "int[] out_hw) -> Tensor")
 _LIB.define("ssim_fwd(Tensor img1, Tensor img2, float[] win, bool size_average, int n_maps) -> (Tensor, Tensor)")
 _LIB.define("ssim_bwd(Tensor img1, Tensor img2, Tensor maps, Tensor grad_out, float[] win, bool size_average, "
             "bool need_d2) -> (Tensor, Tensor)")
+
+MAX_LEVELS = _cabi.MAX_LEVELS
 
 _INT_TO_MODE = {0: "zero", 1: "symmetric", 2: "periodization", 3: "constant", 4: "reflect", 5: "replicate",
                 6: "periodic"}
@@ -151,6 +157,209 @@ def _sfb2d_fake(low, highs, w_lo, w_hi, h_lo, h_hi, mode, out_h, out_w):
     oh = idwt_len(h, len(h_lo), mode) if out_h < 0 else out_h
     ow = idwt_len(w, len(w_lo), mode) if out_w < 0 else out_w
     return low.new_empty((N, C, oh, ow))
+
+
+# ------------------------------------------------------------------------------------------- multi-level chains
+def dwt2_level_dims(H, W, Lh, Lw, mode, J, pad_hw=()):
+    """Output (Ho, Wo) of every level of the analysis chain (host arithmetic)."""
+    dims = []
+    h, w = H, W
+    for j in range(J):
+        ph, pw = (pad_hw[2 * j], pad_hw[2 * j + 1]) if (pad_hw and j > 0) else (0, 0)
+        h, w = coeff_len(h + ph, Lh, mode), coeff_len(w + pw, Lw, mode)
+        dims.append((h, w))
+    return dims
+
+
+def _dwt2_cuda(x, w_lo, w_hi, h_lo, h_hi, mode, J, pad_hw):
+    """J analysis levels in one launch; returns [yl, yh_0 (finest), ..., yh_{J-1}]."""
+    _check_mode(mode)
+    _require_cuda_f32(x, "dwt2")
+    if x.dim() != 4:
+        raise IndexError("b200wave::dwt2 expects a 4-D (N, C, H, W) tensor, got %d-D" % x.dim())
+    if not 1 <= J <= _cabi.MAX_LEVELS:
+        raise RuntimeError("b200wave::dwt2 supports 1..%d levels per call, got %d" % (_cabi.MAX_LEVELS, J))
+    if pad_hw and len(pad_hw) != 2 * J:
+        raise RuntimeError("pad_hw must hold 2*J entries")
+    lib = _cabi.load()
+    N, C, H, W = x.shape
+    Lw, Lh = len(w_lo), len(h_lo)
+    if len(w_hi) != Lw or len(h_hi) != Lh:
+        raise RuntimeError("low- and high-pass filters must have the same length along an axis")
+    dims = dwt2_level_dims(H, W, Lh, Lw, mode, J, pad_hw)
+    lows = [torch.empty((N, C, h, w), device=x.device, dtype=torch.float32) for h, w in dims]
+    highs = [torch.empty((N, C, 3, h, w), device=x.device, dtype=torch.float32) for h, w in dims]
+    if x.numel() == 0 or N * C == 0:
+        return [lows[-1]] + highs
+    xk, ps, rs = _planes_view(x)
+    ws_bytes = lib.b200w_dwt2_workspace_bytes(N * C, J)
+    work = torch.empty((max(ws_bytes, 4) // 4,), device=x.device, dtype=torch.int32)
+    a_wl, _ = _cabi.taps_array(w_lo)
+    a_wh, _ = _cabi.taps_array(w_hi)
+    a_hl, _ = _cabi.taps_array(h_lo)
+    a_hh, _ = _cabi.taps_array(h_hi)
+    pads = _cabi.int_array(pad_hw) if pad_hw else None
+    with torch.cuda.device(x.device):
+        rc = lib.b200w_dwt2_f32(xk.data_ptr(), ps, rs, N * C, H, W, a_wl, a_wh, Lw, a_hl, a_hh, Lh, int(mode), int(J),
+                                pads, _cabi.ptr_array(lows), _cabi.ptr_array(highs), work.data_ptr(), ws_bytes,
+                                _stream())
+    _cabi.check(rc, _mode_name(mode))
+    return [lows[-1]] + highs
+
+
+def _dwt2_fake(x, w_lo, w_hi, h_lo, h_hi, mode, J, pad_hw):
+    N, C, H, W = x.shape
+    dims = dwt2_level_dims(H, W, len(h_lo), len(w_lo), mode, J, pad_hw)
+    return [x.new_empty((N, C) + dims[-1])] + [x.new_empty((N, C, 3) + d) for d in dims]
+
+
+def _idwt2_cuda(yl, yh, hw, w_lo, w_hi, h_lo, h_hi, mode, out_hw):
+    """J synthesis levels in one launch.  hw = 2*J ints (h_j, w_j): sub-band size of level j (yh index, finest
+    first); out_hw = 2*J ints (per-level output size, a crop of the natural one) or [] for the natural sizes."""
+    _check_mode(mode)
+    _require_cuda_f32(yl, "idwt2")
+    if yl.dim() != 4:
+        raise IndexError("b200wave::idwt2 expects a 4-D (N, C, h, w) lowpass tensor, got %d-D" % yl.dim())
+    J = len(yh)
+    if not 1 <= J <= _cabi.MAX_LEVELS:
+        raise RuntimeError("b200wave::idwt2 supports 1..%d levels per call, got %d" % (_cabi.MAX_LEVELS, J))
+    if len(hw) != 2 * J or (out_hw and len(out_hw) != 2 * J):
+        raise RuntimeError("hw / out_hw must hold 2*J entries")
+    lib = _cabi.load()
+    N, C = yl.shape[:2]
+    Lw, Lh = len(w_lo), len(h_lo)
+    if len(w_hi) != Lw or len(h_hi) != Lh:
+        raise RuntimeError("low- and high-pass filters must have the same length along an axis")
+    hs, ws = list(hw[0::2]), list(hw[1::2])
+    if yl.shape[-2] < hs[-1] or yl.shape[-1] < ws[-1]:
+        raise RuntimeError("b200wave::idwt2: yl %s is smaller than the coarsest sub-bands (%d, %d)"
+                           % (tuple(yl.shape), hs[-1], ws[-1]))
+    kept = []
+    for j, h in enumerate(yh):
+        if h is not None:
+            _require_cuda_f32(h, "idwt2")
+            if tuple(h.shape) != (N, C, 3, hs[j], ws[j]):
+                raise RuntimeError("b200wave::idwt2: yh[%d] must have shape %s, got %s"
+                                   % (j, (N, C, 3, hs[j], ws[j]), tuple(h.shape)))
+            h = h.contiguous()
+        kept.append(h)
+    if out_hw:
+        ohs, ows = list(out_hw[0::2]), list(out_hw[1::2])
+    else:
+        ohs = [idwt_len(h, Lh, mode) for h in hs]
+        ows = [idwt_len(w, Lw, mode) for w in ws]
+    ys = [torch.empty((N, C, oh, ow), device=yl.device, dtype=torch.float32) for oh, ow in zip(ohs, ows)]
+    if ys[0].numel() == 0:
+        return ys[0]
+    lk, ps, rs = _planes_view(yl)
+    ws_bytes = lib.b200w_dwt2_workspace_bytes(N * C, J)
+    work = torch.empty((max(ws_bytes, 4) // 4,), device=yl.device, dtype=torch.int32)
+    a_wl, _ = _cabi.taps_array(w_lo)
+    a_wh, _ = _cabi.taps_array(w_hi)
+    a_hl, _ = _cabi.taps_array(h_lo)
+    a_hh, _ = _cabi.taps_array(h_hi)
+    with torch.cuda.device(yl.device):
+        rc = lib.b200w_idwt2_f32(lk.data_ptr(), ps, rs, _cabi.ptr_array(kept), N * C, _cabi.int_array(hs),
+                                 _cabi.int_array(ws), a_wl, a_wh, Lw, a_hl, a_hh, Lh, int(mode), J,
+                                 _cabi.int_array(ohs), _cabi.int_array(ows), _cabi.ptr_array(ys), work.data_ptr(),
+                                 ws_bytes, _stream())
+    _cabi.check(rc, _mode_name(mode))
+    return ys[0]
+
+
+def _idwt2_fake(yl, yh, hw, w_lo, w_hi, h_lo, h_hi, mode, out_hw):
+    N, C = yl.shape[:2]
+    if out_hw:
+        return yl.new_empty((N, C, out_hw[0], out_hw[1]))
+    return yl.new_empty((N, C, idwt_len(hw[0], len(h_lo), mode), idwt_len(hw[1], len(w_lo), mode)))
+
+
+class DWT2Function(torch.autograd.Function):
+    """All J analysis levels of ``DWTForward`` as one autograd node / one launch.  Backward = the chain of the
+    reference's ``AFB2D.backward`` (pw/dwt/lowlevel.py:349-365): synthesis with the same (reversed) analysis taps,
+    every level cropped to the size of the corresponding forward input -- again one launch."""
+
+    @staticmethod
+    def forward(ctx, x, w_lo, w_hi, h_lo, h_hi, mode, J):
+        outs = torch.ops.b200wave.dwt2(x, w_lo, w_hi, h_lo, h_hi, mode, J, [])
+        ctx.taps = (w_lo, w_hi, h_lo, h_hi)
+        ctx.mode = mode
+        ctx.J = J
+        # AFB2D saves only shapes, never x (lowlevel.py:337-338)
+        ctx.in_hw = [tuple(x.shape[-2:])] + [tuple(h.shape[-2:]) for h in outs[1:J]]
+        ctx.sub_hw = [tuple(h.shape[-2:]) for h in outs[1:]]
+        ctx.nc = tuple(x.shape[:2])
+        ctx.set_materialize_grads(False)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, gyl, *gyh):
+        if not ctx.needs_input_grad[0] or (gyl is None and all(g is None for g in gyh)):
+            return (None,) * 7
+        J = ctx.J
+        if gyl is None:
+            ref = next(g for g in gyh if g is not None)
+            gyl = ref.new_zeros(ctx.nc + ctx.sub_hw[-1])
+        w_lo, w_hi, h_lo, h_hi = ctx.taps
+        hw = [v for d in ctx.sub_hw for v in d]
+        out_hw = [v for d in ctx.in_hw for v in d]
+        dx = torch.ops.b200wave.idwt2(gyl, list(gyh), hw, w_lo, w_hi, h_lo, h_hi, ctx.mode, out_hw)
+        return (dx,) + (None,) * 6
+
+
+class IDWT2Function(torch.autograd.Function):
+    """All J synthesis levels of ``DWTInverse`` (incl. the 'unpad' crops, transform2d.py:141-145) as one node / one
+    launch.  Backward = the chain of the reference's ``SFB2D.backward`` (lowlevel.py:682-694): analysis of dy with
+    the un-reversed synthesis taps as correlators; where the forward cropped ll, autograd hands SFB2D.backward the
+    gradient padded with a zero row / column -- reproduced by the kernel's zero extension."""
+
+    @staticmethod
+    def forward(ctx, w_lo, w_hi, h_lo, h_hi, mode, yl, *yh):
+        J = len(yh)
+        Lw, Lh = len(w_lo), len(h_lo)
+        # sub-band size per level: a None entry means "zeros of the current ll size" (transform2d.py:137-139)
+        hw = [None] * J
+        pads = [0] * (2 * J)   # zero extension of the backward chain's level inputs
+        cur = tuple(yl.shape[-2:])
+        for j in range(J - 1, -1, -1):
+            if yh[j] is None:
+                hw[j] = cur
+            else:
+                hw[j] = tuple(yh[j].shape[-2:])
+                if hw[j][0] > cur[0] or hw[j][1] > cur[1]:
+                    raise RuntimeError("DWTInverse: yh[%d] %s is larger than the lowpass it is combined with %s"
+                                       % (j, hw[j], cur))
+            if j < J - 1:   # ll came out of level j+1 with size `cur`; the forward used its top-left hw[j] block
+                pads[2 * (j + 1)], pads[2 * (j + 1) + 1] = cur[0] - hw[j][0], cur[1] - hw[j][1]
+            cur = (idwt_len(hw[j][0], Lh, mode), idwt_len(hw[j][1], Lw, mode))
+        flat_hw = [v for d in hw for v in d]
+        y = torch.ops.b200wave.idwt2(yl, list(yh), flat_hw, w_lo, w_hi, h_lo, h_hi, mode, [])
+        ctx.taps = (w_lo, w_hi, h_lo, h_hi)
+        ctx.mode = mode
+        ctx.J = J
+        ctx.pads = pads
+        ctx.yl_hw = tuple(yl.shape[-2:])
+        ctx.coarse_hw = hw[J - 1]
+        ctx.present = [h is not None for h in yh]
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        J = ctx.J
+        need_l = ctx.needs_input_grad[5]
+        need_h = [ctx.present[j] and ctx.needs_input_grad[6 + j] for j in range(J)]
+        if dy is None or not (need_l or any(need_h)):
+            return (None,) * (6 + J)
+        if max(ctx.pads) > 1:
+            raise RuntimeError("DWTInverse backward: lowpass more than one sample larger than its sub-bands")
+        w_lo, w_hi, h_lo, h_hi = ctx.taps
+        pads = ctx.pads if any(ctx.pads) else []
+        outs = torch.ops.b200wave.dwt2(dy, w_lo, w_hi, h_lo, h_hi, ctx.mode, J, pads)
+        dyl = outs[0] if need_l else None
+        if dyl is not None and tuple(dyl.shape[-2:]) != ctx.yl_hw:   # yl itself was cropped by the forward
+            dyl = torch.nn.functional.pad(dyl, (0, ctx.yl_hw[1] - dyl.shape[-1], 0, ctx.yl_hw[0] - dyl.shape[-2]))
+        dyh = [outs[1 + j] if need_h[j] else None for j in range(J)]
+        return (None,) * 5 + (dyl,) + tuple(dyh)
 
 
 # ------------------------------------------------------------------------------------------- autograd (DWT)
@@ -290,6 +499,8 @@ def _ssim_backward(ctx, dval, dmaps):
 
 _LIB.impl("afb2d", _afb2d_cuda, "CUDA")
 _LIB.impl("sfb2d", _sfb2d_cuda, "CUDA")
+_LIB.impl("dwt2", _dwt2_cuda, "CUDA")
+_LIB.impl("idwt2", _idwt2_cuda, "CUDA")
 _LIB.impl("ssim_fwd", _ssim_fwd_cuda, "CUDA")
 _LIB.impl("ssim_bwd", _ssim_bwd_cuda, "CUDA")
 
@@ -301,11 +512,13 @@ def _cpu_refuse(name):
     return impl
 
 
-for _name in ("afb2d", "sfb2d", "ssim_fwd", "ssim_bwd"):
+for _name in ("afb2d", "sfb2d", "dwt2", "idwt2", "ssim_fwd", "ssim_bwd"):
     _LIB.impl(_name, _cpu_refuse(_name), "CPU")
 
 torch.library.register_fake("b200wave::afb2d", _afb2d_fake, lib=_LIB)
 torch.library.register_fake("b200wave::sfb2d", _sfb2d_fake, lib=_LIB)
+torch.library.register_fake("b200wave::dwt2", _dwt2_fake, lib=_LIB)
+torch.library.register_fake("b200wave::idwt2", _idwt2_fake, lib=_LIB)
 torch.library.register_fake("b200wave::ssim_fwd", _ssim_fwd_fake, lib=_LIB)
 torch.library.register_fake("b200wave::ssim_bwd", _ssim_bwd_fake, lib=_LIB)
 torch.library.register_autograd("b200wave::afb2d", _afb2d_backward, setup_context=_afb2d_setup, lib=_LIB)
@@ -314,5 +527,7 @@ torch.library.register_autograd("b200wave::ssim_fwd", _ssim_backward, setup_cont
 
 afb2d = torch.ops.b200wave.afb2d
 sfb2d = torch.ops.b200wave.sfb2d
+dwt2 = torch.ops.b200wave.dwt2
+idwt2 = torch.ops.b200wave.idwt2
 ssim_fwd = torch.ops.b200wave.ssim_fwd
 ssim_bwd = torch.ops.b200wave.ssim_bwd

@@ -13,6 +13,10 @@
  *                       pw/dwt/lowlevel.py:349-365  AFB2D.backward (same arithmetic + crop to the input H, W)
  *   b200w_ssim_fwd_f32  ssim.py:17-37               _ssim (five 11x11 Gaussian blurs, SSIM map, mean)
  *   b200w_ssim_bwd_f32  autograd through ssim.py:17-37 (closed form)
+ *   b200w_dwt2_f32      pw/dwt/transform2d.py:66-74    the J-level loop of DWTForward.forward over AFB2D.apply,
+ *                       and the backward of DWTInverse (J x SFB2D.backward through the 'unpad' crops) -- ONE launch
+ *   b200w_idwt2_f32     pw/dwt/transform2d.py:134-148  the J-level loop of DWTInverse.forward over SFB2D.apply incl.
+ *                       the 'unpad' crop, and the backward of DWTForward (J x AFB2D.backward) -- ONE launch
  *   b200w_dwt_coeff_len pywt.dwt_coeff_len as called at pw/dwt/lowlevel.py:153
  *
  * Conventions
@@ -45,6 +49,7 @@ extern "C" {
 
 #define B200W_ABI_VERSION 1
 #define B200W_MAX_TAPS 64
+#define B200W_MAX_LEVELS 8
 
 /* mode_to_int, pw/dwt/lowlevel.py:274-290 */
 enum b200w_mode {
@@ -103,6 +108,36 @@ int b200w_sfb2d_f32(const float* low, int64_t low_plane_stride, int64_t low_row_
                     const float* w_lo, const float* w_hi, int Lw,
                     const float* h_lo, const float* h_hi, int Lh,
                     int mode, float* y, int out_h, int out_w, void* stream);
+
+/*
+ * J-level analysis in one launch (J <= B200W_MAX_LEVELS).  Level 0 reads x; level j > 0 reads low[j-1] (dense),
+ * optionally extended by one zero row / column: pad_hw = 2*J ints (pad_h, pad_w per level, entry 0 ignored) or NULL.
+ * The zero extension is what autograd's backward of the 'unpad' slice (transform2d.py:141-145) feeds into
+ * SFB2D.backward.  low[j]: (planes,Ho_j,Wo_j), highs[j]: (planes,3,Ho_j,Wo_j) with
+ * Ho_j = b200w_dwt_coeff_len(Ho_{j-1} + pad_h[j], Lh, mode); low[J-1] is yl, the other low[j] are scratch the
+ * caller provides.  low / highs are HOST arrays of J device pointers.  workspace: DEVICE, at least
+ * b200w_dwt2_workspace_bytes(planes, J) (per-plane completion counters; may be NULL when J == 1).
+ */
+size_t b200w_dwt2_workspace_bytes(int planes, int J);
+int b200w_dwt2_f32(const float* x, int64_t x_plane_stride, int64_t x_row_stride, int planes, int H, int W,
+                   const float* w_lo, const float* w_hi, int Lw,
+                   const float* h_lo, const float* h_hi, int Lh,
+                   int mode, int J, const int* pad_hw, float* const* low, float* const* highs,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * J-level synthesis in one launch.  Levels are indexed like yh (j = 0 finest); the chain runs j = J-1 .. 0.
+ * highs[j]: (planes,3,h[j],w[j]) or NULL (= zeros); highs itself may be NULL.  Level J-1 reads yl (strided, at
+ * least h[J-1] x w[J-1]); level j < J-1 reads the top-left h[j] x w[j] block of y[j+1] (the 'unpad').
+ * y[j]: (planes,out_h[j],out_w[j]) dense with out_h[j] <= b200w_idwt_len(h[j],Lh,mode) (smaller = crop, as in
+ * AFB2D.backward); y[0] is the result, the others are scratch.  h, w, out_h, out_w, highs, y are HOST arrays.
+ */
+int b200w_idwt2_f32(const float* yl, int64_t yl_plane_stride, int64_t yl_row_stride,
+                    const float* const* highs, int planes, const int* h, const int* w,
+                    const float* w_lo, const float* w_hi, int Lw,
+                    const float* h_lo, const float* h_hi, int Lh,
+                    int mode, int J, const int* out_h, const int* out_w, float* const* y,
+                    void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * SSIM forward.  img1,img2: (N,C,H,W) dense.  win: `ws` HOST floats, the normalised 1-D Gaussian

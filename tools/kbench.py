@@ -74,7 +74,7 @@ def ssim_case(n, h, w):
               24 * px / tb / 1e9, 20 * px / (t3 + tb) / 1e9, 20 * px / (t3 + tb) / 1e9 / PEAK * 100), flush=True)
 
 
-what = sys.argv[1] if len(sys.argv) > 1 else "all"
+what = (sys.argv[1] if len(sys.argv) > 1 else "all") if __name__ == "__main__" else "none"
 if what in ("dwt", "all"):
     dwt_case(64, 304, 304, "db3", "symmetric")
     dwt_case(64, 154, 154, "db3", "symmetric")
