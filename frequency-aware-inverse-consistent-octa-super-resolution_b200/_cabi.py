@@ -44,13 +44,14 @@ SYMBOLS = {
     "b200w_sfb2d_f32": (_i, [_vp, _i64, _i64, _vp, _i, _i, _i,
                              _c_float_p, _c_float_p, _i, _c_float_p, _c_float_p, _i,
                              _i, _vp, _i, _i, _vp]),
-    "b200w_dwt2_workspace_bytes": (_sz, [_i, _i]),
+    "b200w_dwt2_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i, _c_int_p]),
     "b200w_dwt2_f32": (_i, [_vp, _i64, _i64, _i, _i, _i,
                             _c_float_p, _c_float_p, _i, _c_float_p, _c_float_p, _i,
-                            _i, _i, _c_int_p, _c_vp_p, _c_vp_p, _vp, _sz, _vp]),
+                            _i, _i, _c_int_p, _vp, _c_vp_p, _vp, _sz, _vp]),
+    "b200w_idwt2_workspace_bytes": (_sz, [_i, _i, _c_int_p, _c_int_p]),
     "b200w_idwt2_f32": (_i, [_vp, _i64, _i64, _c_vp_p, _i, _c_int_p, _c_int_p,
                              _c_float_p, _c_float_p, _i, _c_float_p, _c_float_p, _i,
-                             _i, _i, _c_int_p, _c_int_p, _c_vp_p, _vp, _sz, _vp]),
+                             _i, _i, _c_int_p, _c_int_p, _vp, _vp, _sz, _vp]),
     "b200w_ssim_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "b200w_ssim_fwd_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _c_float_p, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "b200w_ssim_bwd_f32": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _c_float_p, _i, _i, _vp, _vp, _vp]),

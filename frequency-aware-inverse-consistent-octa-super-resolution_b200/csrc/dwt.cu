@@ -24,74 +24,12 @@
 // These are HBM-bound stencils (8 B of traffic per pixel for 2L FMAs): the code keeps the instruction count
 // per pixel low -- 128-bit shared loads feeding register-blocked FMAs whose coefficients come from the
 // constant bank, 64-bit coalesced global stores, staging loops whose addresses advance by constants.
-#include "common.cuh"
+#include "dwt_levels.cuh"
 
 namespace b200w {
 
-constexpr int kMaxLevels = B200W_MAX_LEVELS;
-
-// ------------------------------------------------------------------------------------------------
-// chain bookkeeping shared by the analysis and the synthesis kernels
-// ------------------------------------------------------------------------------------------------
 struct TileRef {
     int level, plane, th, tw;
-};
-
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// make this CTA's global stores (ordered before by a barrier) visible, then count the tile
-__device__ __forceinline__ void signal_done(unsigned* counter) {
-    __threadfence();
-    atomicAdd(counter, 1u);
-}
-
-struct AfbLevel {
-    const float* x;
-    float* low;
-    float* highs;
-    long long x_ps, x_rs;
-    long long tile_base;   // index of this level's first tile in the global tile order
-    int H, W;              // logical input size (including the zero extension below)
-    int Hreal, Wreal;      // rows / columns >= these read as zero (SFB2D.backward through the 'unpad' crop)
-    int Ho, Wo;
-    int offH, offW;
-    int tiles_h, tiles_w;
-    int in_vec;            // widest aligned vector (1, 2 or 4 floats) usable for staging copies
-    int out_vec2;          // 64-bit stores allowed
-};
-
-struct AfbParams {
-    AfbLevel lv[kMaxLevels];
-    long long total;       // tiles over all levels
-    unsigned* done;        // [J][planes] completed-tile counters (null when J == 1)
-    int J, planes, mode;
-    Taps t;
-};
-
-struct SfbLevel {
-    const float* low;
-    const float* highs;    // may be null (= zeros)
-    float* y;
-    long long low_ps, low_rs;
-    long long tile_base;
-    int h, w, out_h, out_w;
-    int offH, offW;
-    int a0H, a0W;          // first A-space coordinate (even) covered by tile 0
-    int tiles_h, tiles_w;
-    int in_vec2;           // 64-bit staging copies allowed
-    int out_vec2;          // 64-bit stores allowed
-};
-
-struct SfbParams {
-    SfbLevel lv[kMaxLevels];  // chain order: coarsest level first
-    long long total;
-    unsigned* done;
-    int J, planes, periodic;
-    Taps t;
 };
 
 template <class P>
@@ -356,18 +294,19 @@ struct AfbOp {
         const int kk = t.tw * TW + 2 * cp;
         const int row0 = t.th * TH + s * RS;
         const size_t band = (size_t)Ho * Wo;
-        float* q0 = lv.low + (size_t)t.plane * band + (size_t)row0 * Wo + kk;
+        const long long lrs = lv.low_rs;
+        float* q0 = lv.low + (long long)t.plane * lv.low_ps + (long long)row0 * lrs + kk;
         float* q1 = lv.highs + (size_t)t.plane * 3 * band + (size_t)row0 * Wo + kk;
         float* q2 = q1 + band;
         float* q3 = q2 + band;
-        if (lv.out_vec2 && row0 + RS <= Ho && kk + 1 < Wo) {  // whole strip inside: 64-bit stores
+        if (lv.out_vec2 && lv.low_vec2 && row0 + RS <= Ho && kk + 1 < Wo) {  // whole strip inside: 64-bit stores
 #pragma unroll
             for (int i = 0; i < RS; ++i) {
                 *reinterpret_cast<float2*>(q0) = acc[i][0];
                 *reinterpret_cast<float2*>(q1) = acc[i][1];
                 *reinterpret_cast<float2*>(q2) = acc[i][2];
                 *reinterpret_cast<float2*>(q3) = acc[i][3];
-                q0 += Wo; q1 += Wo; q2 += Wo; q3 += Wo;
+                q0 += lrs; q1 += Wo; q2 += Wo; q3 += Wo;
             }
         } else if (kk < Wo) {
             const bool second = kk + 1 < Wo;
@@ -377,7 +316,7 @@ struct AfbOp {
                     q0[0] = acc[i][0].x; q1[0] = acc[i][1].x; q2[0] = acc[i][2].x; q3[0] = acc[i][3].x;
                     if (second) { q0[1] = acc[i][0].y; q1[1] = acc[i][1].y; q2[1] = acc[i][2].y; q3[1] = acc[i][3].y; }
                 }
-                q0 += Wo; q1 += Wo; q2 += Wo; q3 += Wo;
+                q0 += lrs; q1 += Wo; q2 += Wo; q3 += Wo;
             }
         }
     }
@@ -419,7 +358,7 @@ __global__ void __launch_bounds__(kThreads) afb2d_direct_kernel(const __grid_con
             hh = fmaf(p.t.h_hi[jh], hi, hh);
         }
         const size_t o = (size_t)i * lv.Wo + k;
-        lv.low[(size_t)plane * band + o] = ll;
+        lv.low[(long long)plane * lv.low_ps + (long long)i * lv.low_rs + k] = ll;
         float* hip = lv.highs + (size_t)plane * 3 * band + o;
         hip[0] = lh;
         hip[band] = hl;
@@ -612,12 +551,13 @@ struct SfbOp {
         const int out_h = lv.out_h, out_w = lv.out_w;
         const int nW = lv.a0W + t.tw * TW + 2 * cp - lv.offW;
         const int nH = lv.a0H + t.th * TH + s * RS - lv.offH;
-        float* q = lv.y + ((long long)t.plane * out_h + nH) * out_w + nW;  // only dereferenced where valid
+        const long long yrs = lv.y_rs;
+        float* q = lv.y + (long long)t.plane * lv.y_ps + (long long)nH * yrs + nW;  // only dereferenced where valid
         if (lv.out_vec2 && nH >= 0 && nH + RS <= out_h && nW >= 0 && nW + 1 < out_w) {
 #pragma unroll
             for (int i = 0; i < RS; ++i) {
                 *reinterpret_cast<float2*>(q) = y[i];
-                q += out_w;
+                q += yrs;
             }
         } else {
             const bool ok0 = nW >= 0 && nW < out_w;
@@ -629,7 +569,7 @@ struct SfbOp {
                     if (ok0) q[0] = y[i].x;
                     if (ok1) q[1] = y[i].y;
                 }
-                q += out_w;
+                q += yrs;
             }
         }
     }
@@ -674,19 +614,27 @@ __global__ void __launch_bounds__(kThreads) sfb2d_direct_kernel(const __grid_con
             y = fmaf(lo, p.t.h_lo[tH], y);
             y = fmaf(hi, p.t.h_hi[tH], y);
         }
-        lv.y[idx] = y;
+        lv.y[(long long)plane * lv.y_ps + (long long)nH * lv.y_rs + nW] = y;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+// B200W_FORCE_DIRECT=1: one-thread-per-output kernels; B200W_FORCE_TILED=1: shared-memory tile kernels instead of
+// the streaming kernels (both are on-device cross-checks of the default path, used by the tests)
+static int env_flag(const char* name) {
+    const char* e = getenv(name);
+    return (e && e[0] == '1') ? 1 : 0;
+}
 static bool force_direct() {
     static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("B200W_FORCE_DIRECT");
-        v = (e && e[0] == '1') ? 1 : 0;
-    }
+    if (v < 0) v = env_flag("B200W_FORCE_DIRECT");
+    return v == 1;
+}
+static bool force_tiled() {
+    static int v = -1;
+    if (v < 0) v = env_flag("B200W_FORCE_TILED");
     return v == 1;
 }
 
@@ -725,9 +673,6 @@ static int analysis_offset(int n, int l, int mode, int* off) {
     return B200W_OK;
 }
 
-static bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
-static int ceil_div(int a, int b) { return (a + b - 1) / b; }
-
 constexpr int kMaxDevices = 64;
 
 struct DeviceInfo {
@@ -751,11 +696,22 @@ static DeviceInfo device_info() {
     return d;
 }
 
-// Persistent launch: grid = min(tiles, SMs x occupancy).  A multi-level chain spins on completion counters, so
-// its CTAs must all be resident: it is launched cooperatively (the runtime refuses the launch otherwise) and
-// the counters are cleared on the stream first.  `occ_cache` is the caller's per-kernel, per-device cache of
-// the occupancy (0 = not queried yet; the query also raises the kernel's dynamic shared-memory limit).  Both are
-// immutable facts about (kernel, device), so caching them keeps the library re-entrant.
+// Workspace layout of a J-level chain: [ticket, done[J][planes]] (u32), then the intermediate low-pass images
+// (planes x rows x pitch floats, pitch = columns rounded up to 4 so that every row is 16-byte aligned), each
+// region rounded up to 256 bytes.  The caller's pointer must be 256-byte aligned (torch allocations are).
+static size_t round256(size_t n) { return (n + 255) & ~(size_t)255; }
+static size_t sync_bytes(int planes, int J) { return J > 1 ? round256(sizeof(unsigned) * ((size_t)J * planes + 1)) : 0; }
+static int pitch4(int w) { return (w + 3) & ~3; }
+static size_t scratch_bytes(int planes, int rows, int cols) {
+    return round256(sizeof(float) * (size_t)planes * rows * pitch4(cols));
+}
+
+// Persistent launch of a tile chain: grid = min(tiles, SMs x occupancy).  A multi-level chain spins on completion
+// counters, so its CTAs must all be resident: it is launched cooperatively (the runtime refuses the launch
+// otherwise) and the counters are cleared on the stream first.  `occ_cache` is the caller's per-kernel,
+// per-device cache of the occupancy (0 = not queried yet; the query also raises the kernel's dynamic
+// shared-memory limit).  Both are immutable facts about (kernel, device), so caching them keeps the library
+// re-entrant.
 template <class Op>
 static int launch_chain(typename Op::Params& p, int* occ_cache, cudaStream_t st) {
     auto kernel = chain_kernel<Op>;
@@ -773,7 +729,7 @@ static int launch_chain(typename Op::Params& p, int* occ_cache, cudaStream_t st)
     if (grid > p.total) grid = p.total;
     cudaError_t e;
     if (p.J > 1) {
-        e = cudaMemsetAsync(p.done, 0, sizeof(unsigned) * (size_t)p.J * p.planes, st);
+        e = cudaMemsetAsync(p.ticket, 0, sizeof(unsigned) * ((size_t)p.J * p.planes + 1), st);
         if (e != cudaSuccess) return set_last_cuda_error(e);
         void* args[] = {(void*)&p};
         e = cudaLaunchCooperativeKernel((const void*)kernel, dim3((unsigned)grid), dim3(Op::NT), args, Op::smem, st);
@@ -843,59 +799,106 @@ static size_t direct_grid(size_t total) {
     return g < 1 ? 1 : (g > cap ? cap : g);
 }
 
-static int tiled_supported(int Lw, int Lh) {
+static bool templated_taps(int Lw, int Lh) {
     return Lw == Lh && (Lw % 2) == 0 && Lw >= 2 && Lw <= 16 && !force_direct();
 }
 
 // ---- analysis chain --------------------------------------------------------------------------------
+// level sizes of the analysis chain; returns a status
+static int afb_dims(int H, int W, int Lw, int Lh, int mode, int J, const int* pad_hw, int* Ho, int* Wo) {
+    int h = H, w = W;
+    for (int j = 0; j < J; ++j) {
+        const int ph = (pad_hw && j > 0) ? pad_hw[2 * j] : 0, pw = (pad_hw && j > 0) ? pad_hw[2 * j + 1] : 0;
+        if (ph < 0 || ph > 1 || pw < 0 || pw > 1) return B200W_ERR_BAD_SHAPE;
+        h = coeff_len(h + ph, Lh, mode);
+        w = coeff_len(w + pw, Lw, mode);
+        if (h < 1 || w < 1) return B200W_ERR_BAD_SHAPE;
+        Ho[j] = h;
+        Wo[j] = w;
+    }
+    return B200W_OK;
+}
+
+static size_t afb_workspace_bytes(int planes, int H, int W, int Lw, int Lh, int mode, int J, const int* pad_hw) {
+    if (planes < 1 || H < 1 || W < 1 || J < 1 || J > kMaxLevels || Lw < 1 || Lh < 1 || !mode_supported(mode)) return 0;
+    int Ho[kMaxLevels], Wo[kMaxLevels];
+    if (afb_dims(H, W, Lw, Lh, mode, J, pad_hw, Ho, Wo)) return 0;
+    size_t n = sync_bytes(planes, J);
+    for (int j = 0; j + 1 < J; ++j) n += scratch_bytes(planes, Ho[j], Wo[j]);
+    return n;
+}
+
 static int run_afb_chain(const float* x, int64_t x_ps, int64_t x_rs, int planes, int H, int W, const float* w_lo,
                          const float* w_hi, int Lw, const float* h_lo, const float* h_hi, int Lh, int mode, int J,
-                         const int* pad_hw, float* const* low, float* const* highs, void* workspace,
-                         size_t workspace_bytes, cudaStream_t st) {
+                         const int* pad_hw, float* yl, float* const* highs, void* workspace, size_t workspace_bytes,
+                         cudaStream_t st) {
     if (!mode_supported(mode)) return B200W_ERR_BAD_MODE;
     if (J < 1 || J > kMaxLevels) return B200W_ERR_BAD_SHAPE;
-    if (!x || !low || !highs) return B200W_ERR_NULL_POINTER;
+    if (!x || !yl || !highs) return B200W_ERR_NULL_POINTER;
     if (planes < 1 || H < 1 || W < 1) return B200W_ERR_BAD_SHAPE;
     AfbParams p;
     int rc = fill_taps(p.t, w_lo, w_hi, Lw, h_lo, h_hi, Lh);
     if (rc) return rc;
+    int Ho[kMaxLevels], Wo[kMaxLevels];
+    if ((rc = afb_dims(H, W, Lw, Lh, mode, J, pad_hw, Ho, Wo))) return rc;
+    if (J > 1) {
+        if (!workspace || workspace_bytes < afb_workspace_bytes(planes, H, W, Lw, Lh, mode, J, pad_hw) ||
+            !aligned_to(workspace, 256))
+            return B200W_ERR_WORKSPACE;
+    }
     p.J = J;
     p.planes = planes;
     p.mode = mode;
-    p.done = nullptr;
+    p.ticket = J > 1 ? (unsigned*)workspace : nullptr;
+    p.done = J > 1 ? p.ticket + 1 : nullptr;
+    char* scratch = (char*)workspace + sync_bytes(planes, J);
     int h = H, w = W;  // real size of the level input
     for (int j = 0; j < J; ++j) {
         AfbLevel& lv = p.lv[j];
-        if (!low[j] || !highs[j]) return B200W_ERR_NULL_POINTER;
+        if (!highs[j]) return B200W_ERR_NULL_POINTER;
         const int ph = (pad_hw && j > 0) ? pad_hw[2 * j] : 0, pw = (pad_hw && j > 0) ? pad_hw[2 * j + 1] : 0;
-        if (ph < 0 || ph > 1 || pw < 0 || pw > 1) return B200W_ERR_BAD_SHAPE;
-        lv.x = j == 0 ? x : low[j - 1];
-        lv.x_ps = j == 0 ? x_ps : (long long)h * w;
-        lv.x_rs = j == 0 ? x_rs : w;
+        if (j == 0) {
+            lv.x = x;
+            lv.x_ps = x_ps;
+            lv.x_rs = x_rs;
+        } else {  // the previous level's low-pass image in the workspace
+            lv.x = p.lv[j - 1].low;
+            lv.x_ps = p.lv[j - 1].low_ps;
+            lv.x_rs = p.lv[j - 1].low_rs;
+        }
         lv.Hreal = h;
         lv.Wreal = w;
         lv.H = h + ph;
         lv.W = w + pw;
         if ((rc = analysis_offset(lv.W, Lw, mode, &lv.offW))) return rc;
         if ((rc = analysis_offset(lv.H, Lh, mode, &lv.offH))) return rc;
-        lv.Ho = coeff_len(lv.H, Lh, mode);
-        lv.Wo = coeff_len(lv.W, Lw, mode);
-        lv.low = low[j];
+        lv.Ho = Ho[j];
+        lv.Wo = Wo[j];
+        if (j == J - 1) {
+            lv.low = yl;
+            lv.low_rs = lv.Wo;
+            lv.low_ps = (long long)lv.Ho * lv.Wo;
+        } else {
+            lv.low = (float*)scratch;
+            lv.low_rs = pitch4(lv.Wo);
+            lv.low_ps = (long long)lv.Ho * lv.low_rs;
+            scratch += scratch_bytes(planes, lv.Ho, lv.Wo);
+        }
         lv.highs = highs[j];
-        // staging vector width: the first staged column of every tile is 2*TW*tw - offW
+        // staging vector width of the tile kernel: the first staged column of every tile is 2*TW*tw - offW
         lv.in_vec = 1;
         if ((lv.offW % 2) == 0 && (lv.x_rs % 2) == 0 && (lv.x_ps % 2) == 0 && aligned_to(lv.x, 8)) lv.in_vec = 2;
         if (lv.in_vec == 2 && (lv.offW % 4) == 0 && (lv.x_rs % 4) == 0 && (lv.x_ps % 4) == 0 && aligned_to(lv.x, 16))
             lv.in_vec = 4;
-        lv.out_vec2 = ((lv.Wo % 2) == 0 && aligned_to(lv.low, 8) && aligned_to(lv.highs, 8)) ? 1 : 0;
+        lv.out_vec2 = ((lv.Wo % 2) == 0 && aligned_to(lv.highs, 8)) ? 1 : 0;
+        lv.low_vec2 = ((lv.low_rs % 2) == 0 && (lv.low_ps % 2) == 0 && aligned_to(lv.low, 8)) ? 1 : 0;
+        lv.tile_base = lv.cta_base = 0;
+        lv.tiles_h = lv.tiles_w = lv.R = lv.ncp = lv.items = lv.cpp = 0;
         h = lv.Ho;
         w = lv.Wo;
     }
-    if (tiled_supported(Lw, Lh)) {
-        if (J > 1) {
-            if (!workspace || workspace_bytes < sizeof(unsigned) * (size_t)J * planes) return B200W_ERR_WORKSPACE;
-            p.done = (unsigned*)workspace;
-        }
+    if (templated_taps(Lw, Lh)) {
+        if (!force_tiled() && afb_stream_supported(p, Lw)) return launch_afb_stream(p, Lw, device_info().sms, st);
         switch (Lw) {
             case 2: return launch_afb_chain<2>(p, st);
             case 4: return launch_afb_chain<4>(p, st);
@@ -923,59 +926,90 @@ static int run_afb_chain(const float* x, int64_t x_ps, int64_t x_rs, int planes,
 }
 
 // ---- synthesis chain -------------------------------------------------------------------------------
+static int sfb_check_dims(int planes, const int* hs, const int* ws, int Lw, int Lh, int mode, int J, const int* out_hs,
+                          const int* out_ws) {
+    if (!mode_supported(mode)) return B200W_ERR_BAD_MODE;
+    if (J < 1 || J > kMaxLevels) return B200W_ERR_BAD_SHAPE;
+    if (!hs || !ws || !out_hs || !out_ws) return B200W_ERR_NULL_POINTER;
+    if (planes < 1 || Lw < 1 || Lh < 1) return B200W_ERR_BAD_SHAPE;
+    const bool per = mode == B200W_MODE_PERIODIZATION;
+    for (int j = 0; j < J; ++j) {
+        if (hs[j] < 1 || ws[j] < 1 || out_hs[j] < 1 || out_ws[j] < 1) return B200W_ERR_BAD_SHAPE;
+        if (per && (2 * hs[j] < Lh || 2 * ws[j] < Lw)) return B200W_ERR_PER_TOO_SHORT;
+        if (out_hs[j] > idwt_len(hs[j], Lh, mode) || out_ws[j] > idwt_len(ws[j], Lw, mode)) return B200W_ERR_BAD_SHAPE;
+        // level j < J-1 reads the top-left h[j] x w[j] block of the previous output ('unpad')
+        if (j + 1 < J && (out_hs[j + 1] < hs[j] || out_ws[j + 1] < ws[j])) return B200W_ERR_BAD_SHAPE;
+    }
+    return B200W_OK;
+}
+
+static size_t sfb_workspace_bytes(int planes, int J, const int* out_hs, const int* out_ws) {
+    size_t n = sync_bytes(planes, J);
+    for (int j = 1; j < J; ++j) n += scratch_bytes(planes, out_hs[j], out_ws[j]);
+    return n;
+}
+
 // levels are given finest first (index j like yh[j]); the chain runs j = J-1 .. 0
 static int run_sfb_chain(const float* yl, int64_t yl_ps, int64_t yl_rs, const float* const* highs, int planes,
                          const int* hs, const int* ws, const float* w_lo, const float* w_hi, int Lw, const float* h_lo,
-                         const float* h_hi, int Lh, int mode, int J, const int* out_hs, const int* out_ws,
-                         float* const* y, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-    if (!mode_supported(mode)) return B200W_ERR_BAD_MODE;
-    if (J < 1 || J > kMaxLevels) return B200W_ERR_BAD_SHAPE;
-    if (!yl || !y || !hs || !ws || !out_hs || !out_ws) return B200W_ERR_NULL_POINTER;
-    if (planes < 1) return B200W_ERR_BAD_SHAPE;
-    SfbParams p;
-    int rc = fill_taps(p.t, w_lo, w_hi, Lw, h_lo, h_hi, Lh);
+                         const float* h_hi, int Lh, int mode, int J, const int* out_hs, const int* out_ws, float* y,
+                         void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    int rc = sfb_check_dims(planes, hs, ws, Lw, Lh, mode, J, out_hs, out_ws);
     if (rc) return rc;
+    if (!yl || !y) return B200W_ERR_NULL_POINTER;
+    SfbParams p;
+    if ((rc = fill_taps(p.t, w_lo, w_hi, Lw, h_lo, h_hi, Lh))) return rc;
+    if (J > 1) {
+        if (!workspace || workspace_bytes < sfb_workspace_bytes(planes, J, out_hs, out_ws) || !aligned_to(workspace, 256))
+            return B200W_ERR_WORKSPACE;
+    }
     const bool per = mode == B200W_MODE_PERIODIZATION;
     p.J = J;
     p.planes = planes;
     p.periodic = per ? 1 : 0;
-    p.done = nullptr;
+    p.ticket = J > 1 ? (unsigned*)workspace : nullptr;
+    p.done = J > 1 ? p.ticket + 1 : nullptr;
+    char* scratch = (char*)workspace + sync_bytes(planes, J);
     for (int c = 0; c < J; ++c) {  // chain position c handles level j = J-1-c
         const int j = J - 1 - c;
         SfbLevel& lv = p.lv[c];
-        const int h = hs[j], w = ws[j];
-        if (h < 1 || w < 1 || out_hs[j] < 1 || out_ws[j] < 1) return B200W_ERR_BAD_SHAPE;
-        if (!y[j]) return B200W_ERR_NULL_POINTER;
-        if (per && (2 * h < Lh || 2 * w < Lw)) return B200W_ERR_PER_TOO_SHORT;
-        if (out_hs[j] > idwt_len(h, Lh, mode) || out_ws[j] > idwt_len(w, Lw, mode)) return B200W_ERR_BAD_SHAPE;
         if (c == 0) {
             lv.low = yl;
             lv.low_ps = yl_ps;
             lv.low_rs = yl_rs;
         } else {  // the previous chain output, of which the top-left h x w block is used ('unpad')
-            if (out_hs[j + 1] < h || out_ws[j + 1] < w) return B200W_ERR_BAD_SHAPE;
-            lv.low = y[j + 1];
-            lv.low_ps = (long long)out_hs[j + 1] * out_ws[j + 1];
-            lv.low_rs = out_ws[j + 1];
+            lv.low = p.lv[c - 1].y;
+            lv.low_ps = p.lv[c - 1].y_ps;
+            lv.low_rs = p.lv[c - 1].y_rs;
         }
         lv.highs = highs ? highs[j] : nullptr;
-        lv.y = y[j];
-        lv.h = h;
-        lv.w = w;
+        lv.h = hs[j];
+        lv.w = ws[j];
         lv.out_h = out_hs[j];
         lv.out_w = out_ws[j];
+        if (j == 0) {
+            lv.y = y;
+            lv.y_rs = lv.out_w;
+            lv.y_ps = (long long)lv.out_h * lv.out_w;
+        } else {
+            lv.y = (float*)scratch;
+            lv.y_rs = pitch4(lv.out_w);
+            lv.y_ps = (long long)lv.out_h * lv.y_rs;
+            scratch += scratch_bytes(planes, lv.out_h, lv.out_w);
+        }
         lv.offW = per ? Lw / 2 - 1 : Lw - 2;
         lv.offH = per ? Lh / 2 - 1 : Lh - 2;
         lv.a0W = lv.a0H = 0;
-        lv.in_vec2 = ((w % 2) == 0 && (lv.low_rs % 2) == 0 && (lv.low_ps % 2) == 0 && aligned_to(lv.low, 8) &&
+        lv.in_vec2 = ((lv.w % 2) == 0 && (lv.low_rs % 2) == 0 && (lv.low_ps % 2) == 0 && aligned_to(lv.low, 8) &&
                       (!lv.highs || aligned_to(lv.highs, 8))) ? 1 : 0;
-        lv.out_vec2 = ((lv.out_w % 2) == 0 && aligned_to(lv.y, 8)) ? 1 : 0;
+        lv.out_vec2 = ((lv.y_rs % 2) == 0 && (lv.y_ps % 2) == 0 && aligned_to(lv.y, 8)) ? 1 : 0;
+        lv.tile_base = lv.cta_base = 0;
+        lv.tiles_h = lv.tiles_w = lv.Rp = lv.nt = lv.items = lv.cpp = 0;
+        lv.q0_off = lv.n0_off = lv.kb_off = lv.m_lo = 0;
+        lv.y_vec = 1;
     }
-    if (tiled_supported(Lw, Lh)) {
-        if (J > 1) {
-            if (!workspace || workspace_bytes < sizeof(unsigned) * (size_t)J * planes) return B200W_ERR_WORKSPACE;
-            p.done = (unsigned*)workspace;
-        }
+    if (templated_taps(Lw, Lh)) {
+        if (!force_tiled() && sfb_stream_supported(p, Lw)) return launch_sfb_stream(p, Lw, device_info().sms, st);
         switch (Lw) {
             case 2: return launch_sfb_chain<2>(p, st);
             case 4: return launch_sfb_chain<4>(p, st);
@@ -1018,9 +1052,16 @@ extern "C" int b200w_idwt_len(int m, int l, int mode) {
     return idwt_len(m, l, mode);
 }
 
-extern "C" size_t b200w_dwt2_workspace_bytes(int planes, int J) {
-    if (planes < 1 || J < 1) return 0;
-    return sizeof(unsigned) * (size_t)planes * (size_t)J;
+extern "C" size_t b200w_dwt2_workspace_bytes(int planes, int H, int W, int Lw, int Lh, int mode, int J,
+                                             const int* pad_hw) {
+    return afb_workspace_bytes(planes, H, W, Lw, Lh, mode, J, pad_hw);
+}
+
+extern "C" size_t b200w_idwt2_workspace_bytes(int planes, int J, const int* out_h, const int* out_w) {
+    if (planes < 1 || J < 1 || J > kMaxLevels || !out_h || !out_w) return 0;
+    for (int j = 0; j < J; ++j)
+        if (out_h[j] < 1 || out_w[j] < 1) return 0;
+    return sfb_workspace_bytes(planes, J, out_h, out_w);
 }
 
 extern "C" int b200w_afb2d_f32(const float* x, int64_t x_plane_stride, int64_t x_row_stride, int planes, int H,
@@ -1028,18 +1069,17 @@ extern "C" int b200w_afb2d_f32(const float* x, int64_t x_plane_stride, int64_t x
                                const float* h_hi, int Lh, int mode, float* low, float* highs, void* stream) {
     if (!mode_supported(mode)) return B200W_ERR_BAD_MODE;
     if (!low || !highs) return B200W_ERR_NULL_POINTER;
-    float* lows[1] = {low};
     float* his[1] = {highs};
     return run_afb_chain(x, x_plane_stride, x_row_stride, planes, H, W, w_lo, w_hi, Lw, h_lo, h_hi, Lh, mode, 1,
-                         nullptr, lows, his, nullptr, 0, (cudaStream_t)stream);
+                         nullptr, low, his, nullptr, 0, (cudaStream_t)stream);
 }
 
 extern "C" int b200w_dwt2_f32(const float* x, int64_t x_plane_stride, int64_t x_row_stride, int planes, int H, int W,
                               const float* w_lo, const float* w_hi, int Lw, const float* h_lo, const float* h_hi,
-                              int Lh, int mode, int J, const int* pad_hw, float* const* low, float* const* highs,
+                              int Lh, int mode, int J, const int* pad_hw, float* yl, float* const* highs,
                               void* workspace, size_t workspace_bytes, void* stream) {
     return run_afb_chain(x, x_plane_stride, x_row_stride, planes, H, W, w_lo, w_hi, Lw, h_lo, h_hi, Lh, mode, J,
-                         pad_hw, low, highs, workspace, workspace_bytes, (cudaStream_t)stream);
+                         pad_hw, yl, highs, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int b200w_sfb2d_f32(const float* low, int64_t low_plane_stride, int64_t low_row_stride,
@@ -1050,15 +1090,14 @@ extern "C" int b200w_sfb2d_f32(const float* low, int64_t low_plane_stride, int64
     if (!low || !y) return B200W_ERR_NULL_POINTER;
     if (planes < 1 || h < 1 || w < 1 || out_h < 1 || out_w < 1) return B200W_ERR_BAD_SHAPE;
     const float* his[1] = {highs};
-    float* ys[1] = {y};
     return run_sfb_chain(low, low_plane_stride, low_row_stride, his, planes, &h, &w, w_lo, w_hi, Lw, h_lo, h_hi, Lh,
-                         mode, 1, &out_h, &out_w, ys, nullptr, 0, (cudaStream_t)stream);
+                         mode, 1, &out_h, &out_w, y, nullptr, 0, (cudaStream_t)stream);
 }
 
 extern "C" int b200w_idwt2_f32(const float* yl, int64_t yl_plane_stride, int64_t yl_row_stride,
                                const float* const* highs, int planes, const int* h, const int* w, const float* w_lo,
                                const float* w_hi, int Lw, const float* h_lo, const float* h_hi, int Lh, int mode,
-                               int J, const int* out_h, const int* out_w, float* const* y, void* workspace,
+                               int J, const int* out_h, const int* out_w, float* y, void* workspace,
                                size_t workspace_bytes, void* stream) {
     return run_sfb_chain(yl, yl_plane_stride, yl_row_stride, highs, planes, h, w, w_lo, w_hi, Lw, h_lo, h_hi, Lh, mode,
                          J, out_h, out_w, y, workspace, workspace_bytes, (cudaStream_t)stream);

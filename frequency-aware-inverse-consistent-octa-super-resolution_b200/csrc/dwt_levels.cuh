@@ -1,0 +1,105 @@
+// Level geometry and chain bookkeeping shared by the DWT kernels (tile, stream and direct variants).
+//
+// A multi-level transform is ONE launch: the work items of all levels form one ordered list (all items of the
+// first level, then the next level, ...).  An item of level j+1 of image plane p may start once every item of
+// level j of that plane has been written: per-(level, plane) completion counters, published with a gpu-scope
+// release (fence + atomic) and consumed with ld.acquire.  Work items are handed out in list order -- by a
+// persistent grid (tile kernels, cooperative launch) or by an atomic ticket taken when a CTA starts (stream
+// kernels) -- so an item only ever waits for items that are already running or done: no deadlock, no launch
+// gaps between the small coarse levels, and the LL intermediates are consumed out of L2.
+#pragma once
+#include "common.cuh"
+
+namespace b200w {
+
+constexpr int kMaxLevels = B200W_MAX_LEVELS;
+constexpr int kStreamNT = 128;   // threads per CTA of the stream kernels
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// make this CTA's global stores (ordered before by a barrier) visible, then count the item
+__device__ __forceinline__ void signal_done(unsigned* counter) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+}
+
+// ---- analysis ------------------------------------------------------------------------------------
+struct AfbLevel {
+    const float* x;
+    float* low;
+    float* highs;          // dense (planes,3,Ho,Wo)
+    long long x_ps, x_rs;  // input plane / row stride (elements)
+    long long low_ps, low_rs;  // LL output strides: dense for the last level, padded scratch for intermediates
+    int H, W;              // logical input size (including the zero extension below)
+    int Hreal, Wreal;      // rows / columns >= these read as zero (SFB2D.backward through the 'unpad' crop)
+    int Ho, Wo;
+    int offH, offW;
+    int out_vec2;          // 64-bit stores into highs allowed
+    int low_vec2;          // 64-bit stores into low allowed
+    // tile kernels
+    long long tile_base;   // index of this level's first tile in the global tile order
+    int tiles_h, tiles_w;
+    int in_vec;            // widest aligned vector (1, 2 or 4 floats) usable for staging copies
+    // stream kernels: a thread owns one pair of output columns over R output rows
+    long long cta_base;    // index of this level's first CTA item
+    int R, ncp, items, cpp;   // rows per segment, column pairs per row, thread items / CTA items per plane
+};
+
+struct AfbParams {
+    AfbLevel lv[kMaxLevels];
+    long long total;       // work items over all levels
+    unsigned* done;        // [J][planes] completed-item counters (null when J == 1)
+    unsigned* ticket;      // stream kernels, J > 1: next work item
+    int J, planes, mode;
+    Taps t;
+};
+
+// ---- synthesis -----------------------------------------------------------------------------------
+struct SfbLevel {
+    const float* low;
+    const float* highs;    // dense (planes,3,h,w); may be null (= zeros)
+    float* y;
+    long long low_ps, low_rs;
+    long long y_ps, y_rs;  // output strides: dense for the last level, padded scratch for intermediates
+    int h, w, out_h, out_w;
+    int offH, offW;
+    // tile kernels
+    long long tile_base;
+    int a0H, a0W;          // first A-space coordinate (even) covered by tile 0
+    int tiles_h, tiles_w;
+    int in_vec2;           // 64-bit staging copies allowed
+    int out_vec2;          // 64-bit stores allowed
+    // stream kernels: a thread owns four adjacent output columns over Rp output row pairs
+    long long cta_base;
+    int Rp, nt, items, cpp;   // row pairs per segment, threads per row, thread items / CTA items per plane
+    int q0_off;            // first coefficient-pair index of thread t: q0 = 2t + q0_off
+    int n0_off;            // first output column of thread t: n0 = 4t + n0_off (0 or -1)
+    int kb_off;            // first loaded coefficient column: kb = 2t + kb_off
+    int m_lo;              // first output row pair (A-space) of the level: offH >> 1
+    int y_vec;             // widest aligned store (1, 2 or 4 floats)
+};
+
+struct SfbParams {
+    SfbLevel lv[kMaxLevels];  // chain order: coarsest level first
+    long long total;
+    unsigned* done;
+    unsigned* ticket;
+    int J, planes, periodic;
+    Taps t;
+};
+
+// launchers of the stream kernels (dwt_stream_afb.cu / dwt_stream_sfb.cu); the level geometry is complete
+// except for the stream work decomposition, which they fill in.  `sms` = SM count of the current device.
+bool afb_stream_supported(const AfbParams& p, int L);
+int launch_afb_stream(AfbParams& p, int L, int sms, cudaStream_t st);
+bool sfb_stream_supported(const SfbParams& p, int L);
+int launch_sfb_stream(SfbParams& p, int L, int sms, cudaStream_t st);
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+}  // namespace b200w

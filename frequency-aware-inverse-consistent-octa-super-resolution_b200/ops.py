@@ -187,24 +187,24 @@ def _dwt2_cuda(x, w_lo, w_hi, h_lo, h_hi, mode, J, pad_hw):
     if len(w_hi) != Lw or len(h_hi) != Lh:
         raise RuntimeError("low- and high-pass filters must have the same length along an axis")
     dims = dwt2_level_dims(H, W, Lh, Lw, mode, J, pad_hw)
-    lows = [torch.empty((N, C, h, w), device=x.device, dtype=torch.float32) for h, w in dims]
+    yl = torch.empty((N, C) + dims[-1], device=x.device, dtype=torch.float32)
     highs = [torch.empty((N, C, 3, h, w), device=x.device, dtype=torch.float32) for h, w in dims]
     if x.numel() == 0 or N * C == 0:
-        return [lows[-1]] + highs
+        return [yl] + highs
     xk, ps, rs = _planes_view(x)
-    ws_bytes = lib.b200w_dwt2_workspace_bytes(N * C, J)
-    work = torch.empty((max(ws_bytes, 4) // 4,), device=x.device, dtype=torch.int32)
+    pads = _cabi.int_array(pad_hw) if pad_hw else None
+    # the intermediate low-pass images and the per-plane completion counters live in the workspace
+    ws_bytes = lib.b200w_dwt2_workspace_bytes(N * C, H, W, Lw, Lh, int(mode), int(J), pads)
+    work = torch.empty((max(ws_bytes, 4),), device=x.device, dtype=torch.uint8)
     a_wl, _ = _cabi.taps_array(w_lo)
     a_wh, _ = _cabi.taps_array(w_hi)
     a_hl, _ = _cabi.taps_array(h_lo)
     a_hh, _ = _cabi.taps_array(h_hi)
-    pads = _cabi.int_array(pad_hw) if pad_hw else None
     with torch.cuda.device(x.device):
         rc = lib.b200w_dwt2_f32(xk.data_ptr(), ps, rs, N * C, H, W, a_wl, a_wh, Lw, a_hl, a_hh, Lh, int(mode), int(J),
-                                pads, _cabi.ptr_array(lows), _cabi.ptr_array(highs), work.data_ptr(), ws_bytes,
-                                _stream())
+                                pads, yl.data_ptr(), _cabi.ptr_array(highs), work.data_ptr(), ws_bytes, _stream())
     _cabi.check(rc, _mode_name(mode))
-    return [lows[-1]] + highs
+    return [yl] + highs
 
 
 def _dwt2_fake(x, w_lo, w_hi, h_lo, h_hi, mode, J, pad_hw):
@@ -248,12 +248,13 @@ def _idwt2_cuda(yl, yh, hw, w_lo, w_hi, h_lo, h_hi, mode, out_hw):
     else:
         ohs = [idwt_len(h, Lh, mode) for h in hs]
         ows = [idwt_len(w, Lw, mode) for w in ws]
-    ys = [torch.empty((N, C, oh, ow), device=yl.device, dtype=torch.float32) for oh, ow in zip(ohs, ows)]
-    if ys[0].numel() == 0:
-        return ys[0]
+    y = torch.empty((N, C, ohs[0], ows[0]), device=yl.device, dtype=torch.float32)
+    if y.numel() == 0:
+        return y
     lk, ps, rs = _planes_view(yl)
-    ws_bytes = lib.b200w_dwt2_workspace_bytes(N * C, J)
-    work = torch.empty((max(ws_bytes, 4) // 4,), device=yl.device, dtype=torch.int32)
+    a_oh, a_ow = _cabi.int_array(ohs), _cabi.int_array(ows)
+    ws_bytes = lib.b200w_idwt2_workspace_bytes(N * C, J, a_oh, a_ow)
+    work = torch.empty((max(ws_bytes, 4),), device=yl.device, dtype=torch.uint8)
     a_wl, _ = _cabi.taps_array(w_lo)
     a_wh, _ = _cabi.taps_array(w_hi)
     a_hl, _ = _cabi.taps_array(h_lo)
@@ -261,10 +262,9 @@ def _idwt2_cuda(yl, yh, hw, w_lo, w_hi, h_lo, h_hi, mode, out_hw):
     with torch.cuda.device(yl.device):
         rc = lib.b200w_idwt2_f32(lk.data_ptr(), ps, rs, _cabi.ptr_array(kept), N * C, _cabi.int_array(hs),
                                  _cabi.int_array(ws), a_wl, a_wh, Lw, a_hl, a_hh, Lh, int(mode), J,
-                                 _cabi.int_array(ohs), _cabi.int_array(ows), _cabi.ptr_array(ys), work.data_ptr(),
-                                 ws_bytes, _stream())
+                                 a_oh, a_ow, y.data_ptr(), work.data_ptr(), ws_bytes, _stream())
     _cabi.check(rc, _mode_name(mode))
-    return ys[0]
+    return y
 
 
 def _idwt2_fake(yl, yh, hw, w_lo, w_hi, h_lo, h_hi, mode, out_hw):

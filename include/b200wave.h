@@ -110,33 +110,37 @@ int b200w_sfb2d_f32(const float* low, int64_t low_plane_stride, int64_t low_row_
                     int mode, float* y, int out_h, int out_w, void* stream);
 
 /*
- * J-level analysis in one launch (J <= B200W_MAX_LEVELS).  Level 0 reads x; level j > 0 reads low[j-1] (dense),
- * optionally extended by one zero row / column: pad_hw = 2*J ints (pad_h, pad_w per level, entry 0 ignored) or NULL.
- * The zero extension is what autograd's backward of the 'unpad' slice (transform2d.py:141-145) feeds into
- * SFB2D.backward.  low[j]: (planes,Ho_j,Wo_j), highs[j]: (planes,3,Ho_j,Wo_j) with
- * Ho_j = b200w_dwt_coeff_len(Ho_{j-1} + pad_h[j], Lh, mode); low[J-1] is yl, the other low[j] are scratch the
- * caller provides.  low / highs are HOST arrays of J device pointers.  workspace: DEVICE, at least
- * b200w_dwt2_workspace_bytes(planes, J) (per-plane completion counters; may be NULL when J == 1).
+ * J-level analysis in one launch (J <= B200W_MAX_LEVELS).  Level 0 reads x; level j > 0 reads the low-pass image
+ * of level j-1, optionally extended by one zero row / column: pad_hw = 2*J ints (pad_h, pad_w per level, entry 0
+ * ignored) or NULL.  The zero extension is what autograd's backward of the 'unpad' slice
+ * (transform2d.py:141-145) feeds into SFB2D.backward.  yl: (planes,Ho_J,Wo_J) dense, highs[j]:
+ * (planes,3,Ho_j,Wo_j) dense, with Ho_j = b200w_dwt_coeff_len(Ho_{j-1} + pad_h[j], Lh, mode); highs is a HOST
+ * array of J device pointers.  The intermediate low-pass images live in `workspace` (DEVICE, 256-byte aligned, at
+ * least b200w_dwt2_workspace_bytes(...) bytes, together with the per-plane completion counters; may be NULL
+ * when J == 1) with rows padded to 16 bytes.
  */
-size_t b200w_dwt2_workspace_bytes(int planes, int J);
+size_t b200w_dwt2_workspace_bytes(int planes, int H, int W, int Lw, int Lh, int mode, int J, const int* pad_hw);
 int b200w_dwt2_f32(const float* x, int64_t x_plane_stride, int64_t x_row_stride, int planes, int H, int W,
                    const float* w_lo, const float* w_hi, int Lw,
                    const float* h_lo, const float* h_hi, int Lh,
-                   int mode, int J, const int* pad_hw, float* const* low, float* const* highs,
+                   int mode, int J, const int* pad_hw, float* yl, float* const* highs,
                    void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * J-level synthesis in one launch.  Levels are indexed like yh (j = 0 finest); the chain runs j = J-1 .. 0.
- * highs[j]: (planes,3,h[j],w[j]) or NULL (= zeros); highs itself may be NULL.  Level J-1 reads yl (strided, at
- * least h[J-1] x w[J-1]); level j < J-1 reads the top-left h[j] x w[j] block of y[j+1] (the 'unpad').
- * y[j]: (planes,out_h[j],out_w[j]) dense with out_h[j] <= b200w_idwt_len(h[j],Lh,mode) (smaller = crop, as in
- * AFB2D.backward); y[0] is the result, the others are scratch.  h, w, out_h, out_w, highs, y are HOST arrays.
+ * highs[j]: (planes,3,h[j],w[j]) dense or NULL (= zeros); highs itself may be NULL.  Level J-1 reads yl (strided,
+ * at least h[J-1] x w[J-1]); level j < J-1 reads the top-left h[j] x w[j] block of the output of level j+1 (the
+ * 'unpad'), whose size is out_h[j+1] x out_w[j+1] <= b200w_idwt_len(h[j+1],Lh,mode) (smaller = crop, as in
+ * AFB2D.backward).  y: (planes,out_h[0],out_w[0]) dense, the result; the intermediate outputs live in `workspace`
+ * (DEVICE, 256-byte aligned, at least b200w_idwt2_workspace_bytes(...) bytes; may be NULL when J == 1).
+ * h, w, out_h, out_w and highs are HOST arrays of J entries.
  */
+size_t b200w_idwt2_workspace_bytes(int planes, int J, const int* out_h, const int* out_w);
 int b200w_idwt2_f32(const float* yl, int64_t yl_plane_stride, int64_t yl_row_stride,
                     const float* const* highs, int planes, const int* h, const int* w,
                     const float* w_lo, const float* w_hi, int Lw,
                     const float* h_lo, const float* h_hi, int Lh,
-                    int mode, int J, const int* out_h, const int* out_w, float* const* y,
+                    int mode, int J, const int* out_h, const int* out_w, float* y,
                     void* workspace, size_t workspace_bytes, void* stream);
 
 /*
