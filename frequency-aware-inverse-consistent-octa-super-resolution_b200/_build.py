@@ -27,7 +27,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3",
     "-cudart", "static",
-]
+] + (["-DB200W_TIMELINE"] if os.environ.get("B200W_TIMELINE") == "1" else [])
 
 
 def find_nvcc():

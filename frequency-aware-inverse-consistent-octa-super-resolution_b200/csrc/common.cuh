@@ -62,6 +62,11 @@ __device__ __forceinline__ int coef_index(int k, int m, bool periodic) {
     return r;
 }
 
+// Out-of-line variants for the stream kernels: the maps are only needed for the few rows / columns outside the
+// image, and every inlined copy costs ~100 instructions (four integer divisions) of instruction-cache footprint.
+static __device__ __noinline__ int ext_index_far(int s, int n, int mode) { return ext_index(s, n, mode); }
+static __device__ __noinline__ int coef_index_far(int k, int m, int periodic) { return coef_index(k, m, periodic != 0); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -28,6 +28,17 @@
 
 namespace b200w {
 
+__global__ void zero_words_kernel(unsigned* w, unsigned n) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) w[i] = 0u;
+}
+
+int zero_sync_words(unsigned* words, size_t n, cudaStream_t st) {
+    zero_words_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(words, (unsigned)n);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? B200W_OK : set_last_cuda_error(e);
+}
+
 struct TileRef {
     int level, plane, th, tw;
 };
@@ -729,8 +740,8 @@ static int launch_chain(typename Op::Params& p, int* occ_cache, cudaStream_t st)
     if (grid > p.total) grid = p.total;
     cudaError_t e;
     if (p.J > 1) {
-        e = cudaMemsetAsync(p.ticket, 0, sizeof(unsigned) * ((size_t)p.J * p.planes + 1), st);
-        if (e != cudaSuccess) return set_last_cuda_error(e);
+        const int rc = zero_sync_words(p.ticket, (size_t)p.J * p.planes + 1, st);
+        if (rc) return rc;
         void* args[] = {(void*)&p};
         e = cudaLaunchCooperativeKernel((const void*)kernel, dim3((unsigned)grid), dim3(Op::NT), args, Op::smem, st);
     } else {
@@ -893,7 +904,7 @@ static int run_afb_chain(const float* x, int64_t x_ps, int64_t x_rs, int planes,
         lv.out_vec2 = ((lv.Wo % 2) == 0 && aligned_to(lv.highs, 8)) ? 1 : 0;
         lv.low_vec2 = ((lv.low_rs % 2) == 0 && (lv.low_ps % 2) == 0 && aligned_to(lv.low, 8)) ? 1 : 0;
         lv.tile_base = lv.cta_base = 0;
-        lv.tiles_h = lv.tiles_w = lv.R = lv.ncp = lv.items = lv.cpp = 0;
+        lv.tiles_h = lv.tiles_w = lv.R = lv.ncp = lv.cpp = lv.cp0A = lv.ncpA = lv.itemsA = lv.cppA = lv.RB = lv.itemsB = 0;
         h = lv.Ho;
         w = lv.Wo;
     }

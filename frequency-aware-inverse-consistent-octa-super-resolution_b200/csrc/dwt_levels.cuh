@@ -21,10 +21,10 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     return v;
 }
 
-// make this CTA's global stores (ordered before by a barrier) visible, then count the item
+// count the item with release semantics: this CTA's global stores (ordered before by a barrier) are visible to
+// whoever acquires the new counter value
 __device__ __forceinline__ void signal_done(unsigned* counter) {
-    __threadfence();
-    atomicAdd(counter, 1u);
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
 }
 
 // ---- analysis ------------------------------------------------------------------------------------
@@ -44,9 +44,13 @@ struct AfbLevel {
     long long tile_base;   // index of this level's first tile in the global tile order
     int tiles_h, tiles_w;
     int in_vec;            // widest aligned vector (1, 2 or 4 floats) usable for staging copies
-    // stream kernels: a thread owns one pair of output columns over R output rows
+    // stream kernels: a thread owns one pair of output columns over R output rows.  Column pairs whose input
+    // window lies inside the image ("interior", cp0A <= cp < cp0A + ncpA) are staged through the per-warp ring;
+    // the few pairs at the left / right border go through the per-thread path with a column map.
     long long cta_base;    // index of this level's first CTA item
-    int R, ncp, items, cpp;   // rows per segment, column pairs per row, thread items / CTA items per plane
+    int R, ncp, cpp;       // rows per segment, column pairs per row, CTA items per plane (= cppA + edge CTAs)
+    int cp0A, ncpA, itemsA, cppA;   // interior class: first pair, pairs per row, thread items, CTA items per plane
+    int RB, itemsB;        // border class: rows per (short) segment, thread items per plane
 };
 
 struct AfbParams {
@@ -98,6 +102,10 @@ bool afb_stream_supported(const AfbParams& p, int L);
 int launch_afb_stream(AfbParams& p, int L, int sms, cudaStream_t st);
 bool sfb_stream_supported(const SfbParams& p, int L);
 int launch_sfb_stream(SfbParams& p, int L, int sms, cudaStream_t st);
+
+// clears the ticket + completion counters of a chain on the stream (a kernel rather than a memset node: inside a
+// CUDA graph a kernel -> memset -> kernel sequence costs several microseconds of engine switching)
+int zero_sync_words(unsigned* words, size_t n, cudaStream_t st);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }

@@ -4,18 +4,25 @@
 // (pw/dwt/lowlevel.py:336-347, 91-172) -- and the J-level loop around it (pw/dwt/transform2d.py:66-74).
 //
 // A thread owns ONE PAIR of adjacent output columns and marches down R output rows of one image plane:
-//   * per input row it loads the 4*NV floats its two outputs need with NV aligned 128-bit loads (a warp reads
-//     512 contiguous bytes; the half-window shared with the neighbouring lane is an L1 hit),
-//   * row pass in registers: lo/hi for both columns, 4L FMAs with the taps as constant-bank operands,
+//   * row pass in registers: per input row the 4*NV floats its two outputs need give lo/hi for both columns,
+//     4L FMAs with the taps as constant-bank operands,
 //   * column pass "accumulate forward": each pair of input rows is scattered into the L/2 output rows it
 //     contributes to (8 accumulators each); the oldest one is complete, is stored with 64-bit coalesced stores
 //     (LL into `low`, LH/HL/HH straight into `highs[:, :, 0..2]`) and its registers are recycled.
-// No shared memory, no barriers, ~2L FMAs + ~1 load/store instruction per input pixel.  The loop is unrolled by
-// lcm(2, L/2) row pairs so that the accumulator ring and the load double buffer have static register names;
-// the loads of the next row pair are issued before the arithmetic of the current one.
-// Segments overlap by L-2 input rows (re-read through L2).  Padding: rows are remapped per row (only in
-// segments that touch the border); lanes whose window leaves [0, W) load element-wise through a precomputed
-// column map (symmetric / reflect / periodic / periodization), "zero" = no load.
+// ~2L FMAs + a handful of memory instructions per input pixel, no block-wide barriers.  The loop is unrolled by
+// L/2 row pairs so that the accumulator ring has static register names.
+//
+// Input staging.  Column pairs whose window lies inside the image ("interior": all but 2..8 per row) are served by
+// a per-WARP ring in shared memory: every lane cp.async-copies its own 16 bytes of each input row (a warp = 512
+// contiguous bytes per row; the last lane of a run adds the NV-1 trailing float4), D row pairs deep, so ~D KB per
+// warp are in flight without holding registers; a lane then reads its window (own float4 + the neighbours')
+// with NV 128-bit shared loads.  Only __syncwarp is needed.  Rows outside the image are remapped per row
+// (symmetric / reflect / periodic / periodization) or zero-filled (cp.async src-size 0).
+// The few border columns of each row run in separate CTAs, one thread per output position, through the row /
+// column maps of the padding mode.
+// Segments overlap by L-2 input rows (re-read through L2).
+#include <algorithm>
+#include <cstdio>
 #include "dwt_levels.cuh"
 
 namespace b200w {
@@ -24,152 +31,289 @@ constexpr int afb_off(int L, bool per) { return per ? L - 1 - L / 2 : L - 2; }
 // the first loaded column is 4*cp - (off + S): S pads the window start down to a multiple of 4
 constexpr int afb_shift(int L, bool per) { return (4 - afb_off(L, per) % 4) % 4; }
 
-template <int NE>
-__device__ __forceinline__ void afb_load_row(float (&v)[NE], const float* xp, long long rs, int r, int H, int Hreal,
-                                             int mode, bool rows_in, bool lane_in, int cb, const int (&cidx)[NE]) {
-    int sr = r;
-    if (!rows_in) {
-        sr = ext_index(r, H, mode);
-        if (sr >= Hreal) sr = -1;
-    }
-    if (sr < 0) {
+// ring geometry: per warp, D stages of one input row pair; a row holds the 32 lanes' own float4 plus NV-1 extra
+// float4 for each run of lanes that sits on one image row (a warp may straddle up to kMaxRuns segment rows)
+constexpr int kMaxRuns = 5;
+constexpr int kMinColPairs = 8;   // interior pairs per row needed for the ring path (=> at most kMaxRuns runs)
+template <int L, int S>
+struct AfbStreamCfg {
+    static constexpr int H2 = L / 2;
+    static constexpr int NV = (S + L + 2 + 3) / 4;   // float4 per window
+    static constexpr int NE = 4 * NV;
+    static constexpr int RP = 32 + kMaxRuns * (NV - 1);   // float4 per ring row
+    static constexpr int D = L <= 8 ? 6 : 4;         // ring depth (row pairs)
+    static constexpr int STAGE = 2 * RP;             // float4 per stage
+    // resident CTAs per SM the ring path is compiled for (caps the registers; the rare border path may spill)
+    static constexpr int MINB = L <= 8 ? 5 : (L <= 12 ? 4 : 3);
+    static constexpr size_t smem = sizeof(float4) * (size_t)(kStreamNT / 32) * D * STAGE;
+};
+
+__device__ __forceinline__ void cp_async16_sz(unsigned dst, const float* src, int bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+
+// source row of input row r: r itself inside the image, else the padding mode's map; -1 = zero row
+__device__ __forceinline__ int afb_src_row(int r, int H, int Hreal, int mode) {
+    if ((unsigned)r < (unsigned)Hreal) return r;
+    const int sr = ext_index_far(r, H, mode);
+    return sr >= Hreal ? -1 : sr;
+}
+
+// one pair of input rows: row pass for both, then scatter into the accumulator ring (ph = pair index mod L/2)
+template <int L, int S, int NE>
+__device__ __forceinline__ void afb_pair_fma(const Taps& t, const float (&v)[2][NE], float (&acc)[L / 2][8], int ph) {
+    constexpr int H2 = L / 2;
+    float rl[2][2], rh[2][2];   // [row of the pair][column]
 #pragma unroll
-        for (int e = 0; e < NE; ++e) v[e] = 0.f;
-        return;
-    }
-    const float* rowp = xp + (long long)sr * rs;
-    if (lane_in) {
-        const float4* q = reinterpret_cast<const float4*>(rowp + cb);
+    for (int e = 0; e < 2; ++e) {
+        float lo0 = 0.f, lo1 = 0.f, hi0 = 0.f, hi1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < NE / 4; ++i) {
-            const float4 t = q[i];
-            v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+        for (int j = 0; j < L; ++j) {
+            lo0 = fmaf(t.w_lo[j], v[e][S + j], lo0);
+            hi0 = fmaf(t.w_hi[j], v[e][S + j], hi0);
+            lo1 = fmaf(t.w_lo[j], v[e][S + j + 2], lo1);
+            hi1 = fmaf(t.w_hi[j], v[e][S + j + 2], hi1);
         }
-    } else {
+        rl[e][0] = lo0; rl[e][1] = lo1; rh[e][0] = hi0; rh[e][1] = hi1;
+    }
+    // this pair carries taps (2u, 2u+1) of output row q - u
 #pragma unroll
-        for (int e = 0; e < NE; ++e) v[e] = cidx[e] >= 0 ? rowp[cidx[e]] : 0.f;
+    for (int u = 0; u < H2; ++u) {
+        const int sl = (ph - u + H2) % H2;
+        const float a = t.h_lo[2 * u], b = t.h_hi[2 * u];
+        const float c = t.h_lo[2 * u + 1], d = t.h_hi[2 * u + 1];
+        float* s = acc[sl];
+        if (u == 0) {   // first contribution: start the accumulators
+            s[0] = a * rl[0][0]; s[1] = a * rl[0][1];
+            s[2] = b * rl[0][0]; s[3] = b * rl[0][1];
+            s[4] = a * rh[0][0]; s[5] = a * rh[0][1];
+            s[6] = b * rh[0][0]; s[7] = b * rh[0][1];
+        } else {
+            s[0] = fmaf(a, rl[0][0], s[0]); s[1] = fmaf(a, rl[0][1], s[1]);
+            s[2] = fmaf(b, rl[0][0], s[2]); s[3] = fmaf(b, rl[0][1], s[3]);
+            s[4] = fmaf(a, rh[0][0], s[4]); s[5] = fmaf(a, rh[0][1], s[5]);
+            s[6] = fmaf(b, rh[0][0], s[6]); s[7] = fmaf(b, rh[0][1], s[7]);
+        }
+        s[0] = fmaf(c, rl[1][0], s[0]); s[1] = fmaf(c, rl[1][1], s[1]);   // LL: W-lo, H-lo
+        s[2] = fmaf(d, rl[1][0], s[2]); s[3] = fmaf(d, rl[1][1], s[3]);   // LH: W-lo, H-hi
+        s[4] = fmaf(c, rh[1][0], s[4]); s[5] = fmaf(c, rh[1][1], s[5]);   // HL: W-hi, H-lo
+        s[6] = fmaf(d, rh[1][0], s[6]); s[7] = fmaf(d, rh[1][1], s[7]);   // HH
     }
 }
 
-template <int L, int S>
-__device__ __forceinline__ void afb_stream_item(const AfbParams& p, const AfbLevel& lv, int plane, int it) {
-    constexpr int H2 = L / 2;
-    constexpr int NV = (S + L + 2 + 3) / 4;
-    constexpr int NE = 4 * NV;
-    constexpr int U = (H2 % 2) ? 2 * H2 : H2;   // lcm(2, H2)
+#ifdef B200W_TIMELINE
+// debug build only (B200W_TIMELINE=1 python -m b200wave._build): per-CTA timestamps of the last chained launch
+__device__ unsigned long long* g_timeline = nullptr;
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define TL_MARK(slot) do { if (g_timeline && threadIdx.x == 0) g_timeline[(size_t)item * 16 + (slot)] = ((slot) == 0 || (slot) == 5) ? gtime() : (unsigned long long)clock64(); } while (0)
+#else
+#define TL_MARK(slot) do { } while (0)
+#endif
 
-    const int seg = it / lv.ncp;
-    const int cp = it - seg * lv.ncp;
+// block until every CTA item of the previous level of this plane has been published (called by all threads,
+// after their index arithmetic so that the set-up overlaps the wait)
+__device__ __forceinline__ void chain_wait(const unsigned* ctr, unsigned need) {
+    if (ctr != nullptr) {
+        if (threadIdx.x == 0)
+            while (ld_acquire_u32(ctr) < need) __nanosleep(20);
+        __syncthreads();
+    }
+}
+
+// ---- interior column pairs: per-warp cp.async ring ---------------------------------------------------
+template <int L, int S>
+__device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel& lv, int plane, int cta, float4* ring_all,
+                                             const unsigned* wait_ctr, unsigned wait_need, unsigned item) {
+    using C = AfbStreamCfg<L, S>;
+    constexpr int H2 = C::H2, NV = C::NV, NE = C::NE, D = C::D;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int it = cta * kStreamNT + tid;
+    const bool active = it < lv.itemsA;
+    const int ncpA = lv.ncpA;
+    const int itc = active ? it : lv.itemsA - 1;     // inactive lanes shadow the last item (no copies, no stores)
+    const int seg = itc / ncpA;
+    const int cpl = itc - seg * ncpA;
+    const int cp = lv.cp0A + cpl;
     const int i0 = seg * lv.R;                       // first output row of the segment
     const int nout = min(lv.R, lv.Ho - i0);
-    const int npairs = nout + H2 - 1;                // input row pairs feeding them
+    const int npairs = active ? nout + H2 - 1 : 0;   // input row pairs feeding them
     const int r0 = 2 * i0 - lv.offH;                 // first input row
     const int H = lv.H, Hreal = lv.Hreal, mode = p.mode;
-    const bool rows_in = r0 >= 0 && r0 + 2 * npairs <= Hreal;
-    const int cb = 4 * cp - (lv.offW + S);           // first loaded column (multiple of 4)
-    const bool lane_in = cb >= 0 && cb + NE <= lv.Wreal;
-    int cidx[NE];
-#pragma unroll
-    for (int e = 0; e < NE; ++e) cidx[e] = 0;
-    if (!lane_in) {
-#pragma unroll
-        for (int e = 0; e < NE; ++e) {
-            const int c = ext_index(cb + e, lv.W, mode);
-            cidx[e] = c >= lv.Wreal ? -1 : c;
-        }
-    }
-    const float* xp = lv.x + (long long)plane * lv.x_ps;
+    const int cb = 4 * cp - (lv.offW + S);           // first column of the window: >= 0, multiple of 4
+    // position in the ring row: own float4 at slot lane + (NV-1)*run; the last lane of a run adds the NV-1 extras
+    const int seg_first = __shfl_sync(0xffffffffu, seg, 0);
+    const int slot = lane + (NV - 1) * (seg - seg_first);
+    const bool run_last = NV > 1 && active && (lane == 31 || cpl == ncpA - 1);
     const long long rs = lv.x_rs;
+    const float* xcol = lv.x + (long long)plane * lv.x_ps + cb;   // column cb of row 0
+    float4* ring = ring_all + (size_t)(tid >> 5) * D * C::STAGE;
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring) + (unsigned)slot * 16u;
+
+    // stage one input row pair (pair index q of this lane's segment) into ring stage `st`
+    // (pairs beyond this lane's segment and zero rows are zero-filled: src-size 0, no branch)
+    auto issue = [&](int q, int st) {
+        const bool live = q < npairs;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int sr = live ? afb_src_row(r0 + 2 * q + e, H, Hreal, mode) : -1;
+            const float* src = xcol + (long long)max(sr, 0) * rs;
+            const int bytes = sr < 0 ? 0 : 16;
+            const unsigned dst = ring_s + (unsigned)((st * 2 + e) * C::RP) * 16u;
+            cp_async16_sz(dst, src, bytes);
+            if (run_last) {
+#pragma unroll
+                for (int k = 1; k < NV; ++k) cp_async16_sz(dst + 16u * k, src + 4 * k, bytes);
+            }
+        }
+    };
 
     const int Wo = lv.Wo;
     const size_t band = (size_t)lv.Ho * Wo;
-    const int k0 = 2 * cp;
-    const bool c1ok = k0 + 1 < Wo;
-    const bool v2lo = lv.low_vec2 && c1ok, v2hi = lv.out_vec2 && c1ok;
+    const bool v2lo = lv.low_vec2 != 0, v2hi = lv.out_vec2 != 0;
     const long long low_rs = lv.low_rs;
-    float* q0 = lv.low + (long long)plane * lv.low_ps + (long long)i0 * low_rs + k0;
-    float* q1 = lv.highs + (size_t)plane * 3 * band + (size_t)i0 * Wo + k0;
+    float* q0 = lv.low + (long long)plane * lv.low_ps + (long long)i0 * low_rs + 2 * cp;
+    float* q1 = lv.highs + (size_t)plane * 3 * band + (size_t)i0 * Wo + 2 * cp;
 
-    float v[2][2][NE];   // [double buffer][row of the pair][window element]
+    // warp-uniform trip count (lanes of a warp may sit in segments of different length)
+    int npw = npairs;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) npw = max(npw, __shfl_xor_sync(0xffffffffu, npw, o));
+
+    chain_wait(wait_ctr, wait_need);
+    TL_MARK(1);
+#pragma unroll 1
+    for (int s = 0; s < D - 1; ++s) {
+        issue(s, s);
+        cp_async_commit();
+    }
+    TL_MARK(14);
     float acc[H2][8];    // ring of pending output rows: LL.x LL.y LH.x LH.y HL.x HL.y HH.x HH.y
-    afb_load_row<NE>(v[0][0], xp, rs, r0, H, Hreal, mode, rows_in, lane_in, cb, cidx);
-    afb_load_row<NE>(v[0][1], xp, rs, r0 + 1, H, Hreal, mode, rows_in, lane_in, cb, cidx);
-
-    for (int qb = 0; qb < npairs; qb += U) {
+    int st_r = 0, st_w = D - 1;
+    for (int qb = 0; qb < npw; qb += H2) {
 #pragma unroll
-        for (int uq = 0; uq < U; ++uq) {
-            const int q = qb + uq;
-            if (q < npairs) {
-                const int cur = uq & 1;
-                const int ph = uq % H2;
-                if (q + 1 < npairs) {   // next pair's loads go out before this pair's arithmetic
-                    afb_load_row<NE>(v[cur ^ 1][0], xp, rs, r0 + 2 * q + 2, H, Hreal, mode, rows_in, lane_in, cb, cidx);
-                    afb_load_row<NE>(v[cur ^ 1][1], xp, rs, r0 + 2 * q + 3, H, Hreal, mode, rows_in, lane_in, cb, cidx);
-                }
-                // row pass (along W, decimated): outputs k0 and k0+1 of both rows of the pair
-                float rl[2][2], rh[2][2];   // [row of the pair][column]
+        for (int ph = 0; ph < H2; ++ph) {
+            const int q = qb + ph;
+            if (q < npw) {   // warp-uniform
+                cp_async_wait<D - 2>();   // this lane's copies of pair q have landed ...
+                __syncwarp();             // ... and everybody's; all lanes are done reading pair q-1
+                if (q < 4) TL_MARK(6 + 2 * q);
+                issue(q + D - 1, st_w);   // refill the stage pair q-1 was read from
+                cp_async_commit();
+                st_w = st_w + 1 == D ? 0 : st_w + 1;
+                {
+                    float v[2][NE];
+                    const float4* src = ring + (st_r * 2) * C::RP + slot;
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    float lo0 = 0.f, lo1 = 0.f, hi0 = 0.f, hi1 = 0.f;
+                    for (int e = 0; e < 2; ++e)
 #pragma unroll
-                    for (int j = 0; j < L; ++j) {
-                        lo0 = fmaf(p.t.w_lo[j], v[cur][e][S + j], lo0);
-                        hi0 = fmaf(p.t.w_hi[j], v[cur][e][S + j], hi0);
-                        lo1 = fmaf(p.t.w_lo[j], v[cur][e][S + j + 2], lo1);
-                        hi1 = fmaf(p.t.w_hi[j], v[cur][e][S + j + 2], hi1);
+                        for (int k = 0; k < NV; ++k) {
+                            const float4 t = src[e * C::RP + k];
+                            v[e][4 * k] = t.x; v[e][4 * k + 1] = t.y; v[e][4 * k + 2] = t.z; v[e][4 * k + 3] = t.w;
+                        }
+                    afb_pair_fma<L, S, NE>(p.t, v, acc, ph);
+                    // output row q - (H2-1) has now seen all its L input rows
+                    if (q >= H2 - 1 && q < npairs) {
+                        const float* s = acc[(ph + 1) % H2];
+                        if (v2lo) {
+                            *reinterpret_cast<float2*>(q0) = make_float2(s[0], s[1]);
+                        } else {
+                            q0[0] = s[0]; q0[1] = s[1];
+                        }
+                        if (v2hi) {
+                            *reinterpret_cast<float2*>(q1) = make_float2(s[2], s[3]);
+                            *reinterpret_cast<float2*>(q1 + band) = make_float2(s[4], s[5]);
+                            *reinterpret_cast<float2*>(q1 + 2 * band) = make_float2(s[6], s[7]);
+                        } else {
+                            q1[0] = s[2]; q1[band] = s[4]; q1[2 * band] = s[6];
+                            q1[1] = s[3]; q1[band + 1] = s[5]; q1[2 * band + 1] = s[7];
+                        }
+                        q0 += low_rs;
+                        q1 += Wo;
                     }
-                    rl[e][0] = lo0; rl[e][1] = lo1; rh[e][0] = hi0; rh[e][1] = hi1;
                 }
-                // column pass: this pair carries taps (2u, 2u+1) of output row q - u
-#pragma unroll
-                for (int u = 0; u < H2; ++u) {
-                    const int slot = (ph - u + H2) % H2;
-                    const float a = p.t.h_lo[2 * u], b = p.t.h_hi[2 * u];
-                    const float c = p.t.h_lo[2 * u + 1], d = p.t.h_hi[2 * u + 1];
-                    float* s = acc[slot];
-                    if (u == 0) {   // first contribution: start the accumulators
-                        s[0] = a * rl[0][0]; s[1] = a * rl[0][1];
-                        s[2] = b * rl[0][0]; s[3] = b * rl[0][1];
-                        s[4] = a * rh[0][0]; s[5] = a * rh[0][1];
-                        s[6] = b * rh[0][0]; s[7] = b * rh[0][1];
-                    } else {
-                        s[0] = fmaf(a, rl[0][0], s[0]); s[1] = fmaf(a, rl[0][1], s[1]);
-                        s[2] = fmaf(b, rl[0][0], s[2]); s[3] = fmaf(b, rl[0][1], s[3]);
-                        s[4] = fmaf(a, rh[0][0], s[4]); s[5] = fmaf(a, rh[0][1], s[5]);
-                        s[6] = fmaf(b, rh[0][0], s[6]); s[7] = fmaf(b, rh[0][1], s[7]);
-                    }
-                    s[0] = fmaf(c, rl[1][0], s[0]); s[1] = fmaf(c, rl[1][1], s[1]);   // LL: W-lo, H-lo
-                    s[2] = fmaf(d, rl[1][0], s[2]); s[3] = fmaf(d, rl[1][1], s[3]);   // LH: W-lo, H-hi
-                    s[4] = fmaf(c, rh[1][0], s[4]); s[5] = fmaf(c, rh[1][1], s[5]);   // HL: W-hi, H-lo
-                    s[6] = fmaf(d, rh[1][0], s[6]); s[7] = fmaf(d, rh[1][1], s[7]);   // HH
-                }
-                // output row q - (H2-1) has now seen all its L input rows
-                if (q >= H2 - 1) {
-                    const float* s = acc[(ph + 1) % H2];
-                    if (v2lo) {
-                        *reinterpret_cast<float2*>(q0) = make_float2(s[0], s[1]);
-                    } else {
-                        q0[0] = s[0];
-                        if (c1ok) q0[1] = s[1];
-                    }
-                    if (v2hi) {
-                        *reinterpret_cast<float2*>(q1) = make_float2(s[2], s[3]);
-                        *reinterpret_cast<float2*>(q1 + band) = make_float2(s[4], s[5]);
-                        *reinterpret_cast<float2*>(q1 + 2 * band) = make_float2(s[6], s[7]);
-                    } else {
-                        q1[0] = s[2]; q1[band] = s[4]; q1[2 * band] = s[6];
-                        if (c1ok) { q1[1] = s[3]; q1[band + 1] = s[5]; q1[2 * band + 1] = s[7]; }
-                    }
-                    q0 += low_rs;
-                    q1 += Wo;
-                }
+                st_r = st_r + 1 == D ? 0 : st_r + 1;
+                if (q < 4) TL_MARK(7 + 2 * q);
             }
         }
     }
+    cp_async_wait<0>();
+}
+
+// ---- border columns: one thread per output position -----------------------------------------------------
+// The 2..8 column pairs per row whose window leaves the image are evaluated directly: thread = (output row,
+// border column); its L x L input samples are independent loads through the row / column maps (one memory
+// latency instead of a dependent march), at the price of recomputing the row pass L/2 times -- for < 3 % of
+// the outputs.
+template <int L, int S>
+__device__ __forceinline__ void afb_border_item(const AfbParams& p, const AfbLevel& lv, int plane, int it) {
+    const int ncB = lv.Wo - 2 * lv.ncpA;             // border columns per output row
+    const int i = it / ncB;
+    const int e0 = it - i * ncB;
+    const int k = e0 < 2 * lv.cp0A ? e0 : e0 + 2 * lv.ncpA;   // left border columns, then right border columns
+    const int mode = p.mode;
+    int cidx[L];
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+        int c = 2 * k + j - lv.offW;
+        if ((unsigned)c >= (unsigned)lv.Wreal) {
+            c = ext_index_far(c, lv.W, mode);
+            if (c >= lv.Wreal) c = -1;
+        }
+        cidx[j] = c;
+    }
+    const float* xp = lv.x + (long long)plane * lv.x_ps;
+    // all L x L samples are loaded before any arithmetic (clamped address + select instead of branches), so
+    // the thread pays one memory round trip; rows are done in chunks of <= 6 to bound the registers
+    float ll = 0.f, lh = 0.f, hl = 0.f, hh = 0.f;
+    constexpr int CH = L < 6 ? L : 6;
+#pragma unroll
+    for (int j0 = 0; j0 < L; j0 += CH) {
+        float v[CH][L];
+        bool rok[CH];
+#pragma unroll
+        for (int jj = 0; jj < CH; ++jj) {
+            const int jh = j0 + jj;
+            const int sr = jh < L ? afb_src_row(2 * i + jh - lv.offH, lv.H, lv.Hreal, mode) : -1;
+            rok[jj] = sr >= 0;
+            const float* rowp = xp + (long long)max(sr, 0) * lv.x_rs;
+#pragma unroll
+            for (int j = 0; j < L; ++j) v[jj][j] = rowp[max(cidx[j], 0)];
+        }
+#pragma unroll
+        for (int jj = 0; jj < CH; ++jj) {
+            const int jh = j0 + jj;
+            if (jh < L) {
+                float lo = 0.f, hi = 0.f;
+#pragma unroll
+                for (int j = 0; j < L; ++j) {
+                    const float x = (rok[jj] && cidx[j] >= 0) ? v[jj][j] : 0.f;
+                    lo = fmaf(p.t.w_lo[j], x, lo);
+                    hi = fmaf(p.t.w_hi[j], x, hi);
+                }
+                ll = fmaf(p.t.h_lo[jh], lo, ll);
+                lh = fmaf(p.t.h_hi[jh], lo, lh);
+                hl = fmaf(p.t.h_lo[jh], hi, hl);
+                hh = fmaf(p.t.h_hi[jh], hi, hh);
+            }
+        }
+    }
+    const size_t band = (size_t)lv.Ho * lv.Wo;
+    const size_t o = (size_t)i * lv.Wo + k;
+    lv.low[(long long)plane * lv.low_ps + (long long)i * lv.low_rs + k] = ll;
+    float* hip = lv.highs + (size_t)plane * 3 * band + o;
+    hip[0] = lh;
+    hip[band] = hl;
+    hip[2 * band] = hh;
 }
 
 template <int L, int S>
-__global__ void __launch_bounds__(kStreamNT) afb_stream_kernel(const __grid_constant__ AfbParams p) {
+__global__ void __launch_bounds__(kStreamNT, AfbStreamCfg<L, S>::MINB) afb_stream_kernel(const __grid_constant__ AfbParams p) {
+    extern __shared__ float4 ring_all[];
     __shared__ unsigned s_item;
     const int tid = threadIdx.x;
     unsigned item = blockIdx.x;
@@ -184,30 +328,46 @@ __global__ void __launch_bounds__(kStreamNT) afb_stream_kernel(const __grid_cons
     const AfbLevel& lv = p.lv[level];
     const unsigned local = item - (unsigned)lv.cta_base;
     const int plane = (int)(local / (unsigned)lv.cpp);
-    const int c = (int)(local - (unsigned)plane * (unsigned)lv.cpp);
-    if (level > 0) {   // the previous level of this plane must be complete
-        if (tid == 0) {
-            const unsigned need = (unsigned)p.lv[level - 1].cpp;
-            const unsigned* ctr = p.done + (size_t)(level - 1) * p.planes + plane;
-            while (ld_acquire_u32(ctr) < need) __nanosleep(100);
-        }
-        __syncthreads();
+    const int cta = (int)(local - (unsigned)plane * (unsigned)lv.cpp);
+    TL_MARK(0);
+    TL_MARK(15);
+#ifdef B200W_TIMELINE
+    if (g_timeline && tid == 0) {
+        g_timeline[(size_t)item * 16 + 3] = ((unsigned long long)level << 48) | ((unsigned long long)plane << 24) | (unsigned)cta;
+        unsigned smid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        g_timeline[(size_t)item * 16 + 4] = smid | ((unsigned long long)(cta < lv.cppA ? 0 : 1) << 32);
     }
-    const int it = c * kStreamNT + tid;
-    if (it < lv.items) afb_stream_item<L, S>(p, lv, plane, it);
+#endif
+    // the previous level of this plane must be complete before its low-pass image is read
+    const unsigned* wait_ctr = level > 0 ? p.done + (size_t)(level - 1) * p.planes + plane : nullptr;
+    const unsigned wait_need = level > 0 ? (unsigned)p.lv[level - 1].cpp : 0u;
+    if (cta < lv.cppA) {
+        afb_ring_cta<L, S>(p, lv, plane, cta, ring_all, wait_ctr, wait_need, item);
+    } else {
+        chain_wait(wait_ctr, wait_need);
+        TL_MARK(1);
+        const int it = (cta - lv.cppA) * kStreamNT + tid;
+        if (it < lv.itemsB) afb_border_item<L, S>(p, lv, plane, it);
+    }
+    TL_MARK(2);
     if (level + 1 < p.J) {
         __syncthreads();
         if (tid == 0) signal_done(p.done + (size_t)level * p.planes + plane);
     }
+    TL_MARK(5);
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    if (!e || !*e) return dflt;
+    const int v = atoi(e);
+    return v > 0 ? v : dflt;
+}
+// tuning knob (read once): rows per segment override
 static int stream_rows_override() {
     static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("B200W_STREAM_ROWS");
-        v = e ? atoi(e) : 0;
-        if (v < 0) v = 0;
-    }
+    if (v < 0) v = env_int("B200W_STREAM_ROWS", 0);
     return v;
 }
 
@@ -224,35 +384,76 @@ bool afb_stream_supported(const AfbParams& p, int L) {
 
 template <int L, int S>
 static int launch_afb_stream_t(AfbParams& p, int sms, cudaStream_t st) {
+    using C = AfbStreamCfg<L, S>;
     constexpr int H2 = L / 2;
-    // enough thread items for ~12 warps per SM, but segments long enough to amortise the L-2 warm-up rows
-    const long long target = (long long)sms * 32 * 12;
-    const int rmin = H2 > 1 ? 4 * (H2 - 1) : 4;
+    // Segments of ~16 output rows (longer for long filters, to amortise the L-2 warm-up rows): many short work
+    // items balance better than one wave of long ones (measured, profiles/r01_sweep_rows.log).  A level that
+    // cannot fill the resident CTA slots anyway is latency-bound (per-CTA set-up + one dependent row pair after
+    // the other): it gets shorter segments, down to 2 rows for the small dependent levels of a chain.
+    const int rpref = std::max(16, 4 * (H2 - 1));
+    const long long slots = (long long)sms * C::MINB;
     long long base = 0;
     for (int j = 0; j < p.J; ++j) {
         AfbLevel& lv = p.lv[j];
         lv.ncp = ceil_div(lv.Wo, 2);
-        const long long rowitems = (long long)p.planes * lv.ncp;
-        long long nseg_want = (target + rowitems - 1) / rowitems;
-        if (nseg_want < 1) nseg_want = 1;
-        int R = (int)((lv.Ho + nseg_want - 1) / nseg_want);
-        if (R < rmin) R = rmin;
+        // interior column pairs: window [4cp - (offW+S), +NE) inside [0, Wreal) and both output columns valid
+        lv.cp0A = (lv.offW + S) / 4;
+        int cpR = (lv.Wreal + lv.offW + S - C::NE) / 4 + 1;   // first pair whose window leaves the image
+        if (lv.Wreal + lv.offW + S - C::NE < 0) cpR = 0;
+        if (cpR > lv.Wo / 2) cpR = lv.Wo / 2;
+        lv.ncpA = cpR - lv.cp0A;
+        if (lv.ncpA < kMinColPairs) lv.ncpA = 0;              // too narrow for the ring: all columns take the border path
+        // level 0 keeps the preferred length (measured best even when it leaves CTA slots empty); the dependent
+        // levels of a chain shrink until they fill the slots
+        int R = rpref;
+        if (j > 0) {
+            const int rmin = std::max(2, H2 - 1);
+            while (R > rmin && (long long)p.planes * ceil_div(ceil_div(lv.Ho, R) * std::max(lv.ncpA, 1), kStreamNT) < slots)
+                R = std::max(rmin, R - 2);
+        }
         if (stream_rows_override() > 0) R = stream_rows_override();
+        if (j > 0 && env_int("B200W_STREAM_ROWS_HI", 0) > 0) R = env_int("B200W_STREAM_ROWS_HI", 0);
         if (R > lv.Ho) R = lv.Ho;
         lv.R = R;
-        lv.items = ceil_div(lv.Ho, R) * lv.ncp;
-        lv.cpp = ceil_div(lv.items, kStreamNT);
+        const int nseg = ceil_div(lv.Ho, R);
+        lv.itemsA = nseg * lv.ncpA;
+        lv.RB = 1;
+        lv.itemsB = lv.Ho * (lv.Wo - 2 * lv.ncpA);   // border columns: one thread per output position
+        lv.cppA = ceil_div(lv.itemsA, kStreamNT);
+        lv.cpp = lv.cppA + ceil_div(lv.itemsB, kStreamNT);
         lv.cta_base = base;
         base += (long long)lv.cpp * p.planes;
     }
     p.total = base;
     if (base > 0x7fffffffLL) return B200W_ERR_BAD_SHAPE;
-    if (p.J > 1) {
-        cudaError_t e = cudaMemsetAsync(p.ticket, 0, sizeof(unsigned) * ((size_t)p.J * p.planes + 1), st);
-        if (e != cudaSuccess) return set_last_cuda_error(e);
+    {   // timing experiment only (results incomplete): run just the first k levels of the chain
+        const int k = env_int("B200W_DEBUG_LEVELS", 0);
+        if (k > 0 && k < p.J) base = p.lv[k].cta_base;
     }
-    afb_stream_kernel<L, S><<<(unsigned)base, kStreamNT, 0, st>>>(p);
+    if (p.J > 1) {
+        const int rc = zero_sync_words(p.ticket, (size_t)p.J * p.planes + 1, st);
+        if (rc) return rc;
+    }
+#ifdef B200W_TIMELINE
+    static unsigned long long* tl = nullptr;
+    const char* tl_path = getenv("B200W_TIMELINE_FILE");
+    if (tl_path) {
+        if (!tl) cudaMalloc(&tl, sizeof(unsigned long long) * 16 * 65536);
+        cudaMemsetAsync(tl, 0, sizeof(unsigned long long) * 16 * 65536, st);
+        cudaMemcpyToSymbolAsync(g_timeline, &tl, sizeof(tl), 0, cudaMemcpyHostToDevice, st);
+    }
+#endif
+    afb_stream_kernel<L, S><<<(unsigned)base, kStreamNT, C::smem, st>>>(p);
     const cudaError_t e = cudaGetLastError();
+#ifdef B200W_TIMELINE
+    if (tl_path && base <= 65536) {
+        cudaStreamSynchronize(st);
+        static unsigned long long host[16 * 65536];
+        cudaMemcpy(host, tl, sizeof(unsigned long long) * 16 * (size_t)base, cudaMemcpyDeviceToHost);
+        FILE* f = fopen(tl_path, "wb");
+        if (f) { fwrite(host, sizeof(unsigned long long) * 16, (size_t)base, f); fclose(f); }
+    }
+#endif
     return e == cudaSuccess ? B200W_OK : set_last_cuda_error(e);
 }
 

@@ -300,8 +300,8 @@ static int launch_sfb_stream_t(SfbParams& p, int sms, cudaStream_t st) {
     p.total = base;
     if (base > 0x7fffffffLL) return B200W_ERR_BAD_SHAPE;
     if (p.J > 1) {
-        cudaError_t e = cudaMemsetAsync(p.ticket, 0, sizeof(unsigned) * ((size_t)p.J * p.planes + 1), st);
-        if (e != cudaSuccess) return set_last_cuda_error(e);
+        const int rc = zero_sync_words(p.ticket, (size_t)p.J * p.planes + 1, st);
+        if (rc) return rc;
     }
     sfb_stream_kernel<L, V, S2><<<(unsigned)base, kStreamNT, 0, st>>>(p);
     const cudaError_t e = cudaGetLastError();
