@@ -1015,8 +1015,8 @@ static int run_sfb_chain(const float* yl, int64_t yl_ps, int64_t yl_rs, const fl
                       (!lv.highs || aligned_to(lv.highs, 8))) ? 1 : 0;
         lv.out_vec2 = ((lv.y_rs % 2) == 0 && (lv.y_ps % 2) == 0 && aligned_to(lv.y, 8)) ? 1 : 0;
         lv.tile_base = lv.cta_base = 0;
-        lv.tiles_h = lv.tiles_w = lv.Rp = lv.nt = lv.items = lv.cpp = 0;
-        lv.q0_off = lv.n0_off = lv.kb_off = lv.m_lo = 0;
+        lv.tiles_h = lv.tiles_w = lv.Rp = lv.cpp = lv.tA0 = lv.ntA = lv.itemsA = lv.cppA = 0;
+        lv.nA0 = lv.nA1 = lv.itemsB = lv.n0_off = lv.kb_off = lv.m_lo = lv.vec2 = 0;
         lv.y_vec = 1;
     }
     if (templated_taps(Lw, Lh)) {

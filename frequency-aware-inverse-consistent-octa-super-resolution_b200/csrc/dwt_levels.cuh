@@ -77,14 +77,18 @@ struct SfbLevel {
     int tiles_h, tiles_w;
     int in_vec2;           // 64-bit staging copies allowed
     int out_vec2;          // 64-bit stores allowed
-    // stream kernels: a thread owns four adjacent output columns over Rp output row pairs
+    // stream kernels: a thread owns four adjacent output columns over Rp output row pairs.  Threads whose
+    // coefficient window and outputs lie inside the arrays ("interior", tA0 <= t < tA0 + ntA) stage through the
+    // per-warp ring; the few border output columns are evaluated one thread per output position.
     long long cta_base;
-    int Rp, nt, items, cpp;   // row pairs per segment, threads per row, thread items / CTA items per plane
-    int q0_off;            // first coefficient-pair index of thread t: q0 = 2t + q0_off
+    int Rp, cpp;           // row pairs per segment, CTA items per plane (= cppA + border CTAs)
+    int tA0, ntA, itemsA, cppA;   // interior class: first thread, threads per row, thread items / CTA items per plane
+    int nA0, nA1, itemsB;  // border class: output columns [0,nA0) and [nA1,out_w); thread items per plane
     int n0_off;            // first output column of thread t: n0 = 4t + n0_off (0 or -1)
-    int kb_off;            // first loaded coefficient column: kb = 2t + kb_off
+    int kb_off;            // first staged coefficient column of thread t: kb = 2t + kb_off
     int m_lo;              // first output row pair (A-space) of the level: offH >> 1
     int y_vec;             // widest aligned store (1, 2 or 4 floats)
+    int vec2;              // coefficient rows are 8-byte aligned: stage with 64-bit copies
 };
 
 struct SfbParams {

@@ -17,7 +17,7 @@
 // contiguous bytes per row; the last lane of a run adds the NV-1 trailing float4), D row pairs deep, so ~D KB per
 // warp are in flight without holding registers; a lane then reads its window (own float4 + the neighbours')
 // with NV 128-bit shared loads.  Only __syncwarp is needed.  Rows outside the image are remapped per row
-// (symmetric / reflect / periodic / periodization) or zero-filled (cp.async src-size 0).
+// (symmetric / reflect / periodic / periodization) or cleared with shared stores.
 // The few border columns of each row run in separate CTAs, one thread per output position, through the row /
 // column maps of the padding mode.
 // Segments overlap by L-2 input rows (re-read through L2).
@@ -48,10 +48,6 @@ struct AfbStreamCfg {
     static constexpr size_t smem = sizeof(float4) * (size_t)(kStreamNT / 32) * D * STAGE;
 };
 
-__device__ __forceinline__ void cp_async16_sz(unsigned dst, const float* src, int bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
-}
-
 // source row of input row r: r itself inside the image, else the padding mode's map; -1 = zero row
 __device__ __forceinline__ int afb_src_row(int r, int H, int Hreal, int mode) {
     if ((unsigned)r < (unsigned)Hreal) return r;
@@ -60,9 +56,13 @@ __device__ __forceinline__ int afb_src_row(int r, int H, int Hreal, int mode) {
 }
 
 // one pair of input rows: row pass for both, then scatter into the accumulator ring (ph = pair index mod L/2)
+// With kRotate the ring is kept in age order instead (slot 0 = oldest) and shifted by the caller after the store:
+// L/2-1 register moves per row pair, but the loop needs no unrolling by L/2 -- for long filters the unrolled
+// body would not fit the instruction cache.
 template <int L, int S, int NE>
 __device__ __forceinline__ void afb_pair_fma(const Taps& t, const float (&v)[2][NE], float (&acc)[L / 2][8], int ph) {
     constexpr int H2 = L / 2;
+    constexpr bool kRotate = L >= 10;
     float rl[2][2], rh[2][2];   // [row of the pair][column]
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
@@ -79,7 +79,7 @@ __device__ __forceinline__ void afb_pair_fma(const Taps& t, const float (&v)[2][
     // this pair carries taps (2u, 2u+1) of output row q - u
 #pragma unroll
     for (int u = 0; u < H2; ++u) {
-        const int sl = (ph - u + H2) % H2;
+        const int sl = kRotate ? H2 - 1 - u : (ph - u + H2) % H2;
         const float a = t.h_lo[2 * u], b = t.h_hi[2 * u];
         const float c = t.h_lo[2 * u + 1], d = t.h_hi[2 * u + 1];
         float* s = acc[sl];
@@ -154,20 +154,32 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
     float4* ring = ring_all + (size_t)(tid >> 5) * D * C::STAGE;
     const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring) + (unsigned)slot * 16u;
 
-    // stage one input row pair (pair index q of this lane's segment) into ring stage `st`
-    // (pairs beyond this lane's segment and zero rows are zero-filled: src-size 0, no branch)
+    // stage one input row pair (pair index q of this lane's segment) into ring stage `st`.  Rows inside the image
+    // take the plain 16-byte cp.async (the zero-filling form costs three padding instructions each); zero rows
+    // are cleared with shared stores.
     auto issue = [&](int q, int st) {
-        const bool live = q < npairs;
+        // nothing is staged beyond this lane's segment: the lanes that would read those slots (same run, same
+        // segment) are past their last pair too, and an idle lane must not touch slots that belong to others
+        if (q < npairs) {
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int sr = live ? afb_src_row(r0 + 2 * q + e, H, Hreal, mode) : -1;
-            const float* src = xcol + (long long)max(sr, 0) * rs;
-            const int bytes = sr < 0 ? 0 : 16;
-            const unsigned dst = ring_s + (unsigned)((st * 2 + e) * C::RP) * 16u;
-            cp_async16_sz(dst, src, bytes);
-            if (run_last) {
+            for (int e = 0; e < 2; ++e) {
+                const int sr = afb_src_row(r0 + 2 * q + e, H, Hreal, mode);
+                const unsigned dst = ring_s + (unsigned)((st * 2 + e) * C::RP) * 16u;
+                if (sr >= 0) {
+                    const float* src = xcol + (long long)sr * rs;
+                    cp_async<4>(dst, src);
+                    if (run_last) {
 #pragma unroll
-                for (int k = 1; k < NV; ++k) cp_async16_sz(dst + 16u * k, src + 4 * k, bytes);
+                        for (int k = 1; k < NV; ++k) cp_async<4>(dst + 16u * k, src + 4 * k);
+                    }
+                } else {
+                    float4* d = ring + (st * 2 + e) * C::RP + slot;
+                    d[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (run_last) {
+#pragma unroll
+                        for (int k = 1; k < NV; ++k) d[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
             }
         }
     };
@@ -194,9 +206,11 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
     TL_MARK(14);
     float acc[H2][8];    // ring of pending output rows: LL.x LL.y LH.x LH.y HL.x HL.y HH.x HH.y
     int st_r = 0, st_w = D - 1;
-    for (int qb = 0; qb < npw; qb += H2) {
+    constexpr bool kRotate = L >= 10;
+    constexpr int UQ = kRotate ? 1 : H2;
+    for (int qb = 0; qb < npw; qb += UQ) {
 #pragma unroll
-        for (int ph = 0; ph < H2; ++ph) {
+        for (int ph = 0; ph < UQ; ++ph) {
             const int q = qb + ph;
             if (q < npw) {   // warp-uniform
                 cp_async_wait<D - 2>();   // this lane's copies of pair q have landed ...
@@ -218,7 +232,7 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
                     afb_pair_fma<L, S, NE>(p.t, v, acc, ph);
                     // output row q - (H2-1) has now seen all its L input rows
                     if (q >= H2 - 1 && q < npairs) {
-                        const float* s = acc[(ph + 1) % H2];
+                        const float* s = acc[kRotate ? 0 : (ph + 1) % H2];
                         if (v2lo) {
                             *reinterpret_cast<float2*>(q0) = make_float2(s[0], s[1]);
                         } else {
@@ -234,6 +248,12 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
                         }
                         q0 += low_rs;
                         q1 += Wo;
+                    }
+                    if (kRotate) {
+#pragma unroll
+                        for (int k = 0; k + 1 < H2; ++k)
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) acc[k][i] = acc[k + 1][i];
                     }
                 }
                 st_r = st_r + 1 == D ? 0 : st_r + 1;

@@ -7,13 +7,20 @@
 // "A-space": a = n + off (off = L-2, periodization L/2-1), so output a uses taps of parity a&1 only:
 //     y[a] = sum_u c[(a>>1) - u] * g[(a&1) + 2u],  u = 0 .. L/2-1            (the polyphase form of sfb1d)
 // A thread owns FOUR adjacent output columns (two coefficient pairs) and marches down Rp output row pairs:
-//   * per coefficient row it loads L/2+1 coefficients of each of the four sub-bands (64-bit loads when the
-//     rows are 8-byte aligned, else 32-bit),
-//   * W synthesis in registers: 4 outputs for the h_lo branch (LL, HL) and 4 for the h_hi branch (LH, HH),
-//   * H synthesis "accumulate forward": the row is scattered into the L/2 output row pairs it contributes to
-//     (8 accumulators each); the oldest pair is complete and is written with 128-bit coalesced stores.
-// No shared memory, no barriers.  Coefficients outside the sub-band are zero (periodization: wrap around); a
-// null `highs` means zeros (transform2d.py:137-139); out_h / out_w smaller than the natural size crop.
+//   * W synthesis in registers: the L/2+1 coefficients of each of the four sub-bands in its window give 4 outputs
+//     for the h_lo branch (LL, HL) and 4 for the h_hi branch (LH, HH),
+//   * H synthesis "accumulate forward": the coefficient row is scattered into the L/2 output row pairs it
+//     contributes to (8 accumulators each); the oldest pair is complete and is written with 128-bit stores.
+// The loop is unrolled by L/2 rows so that the accumulator ring has static register names.
+//
+// Input staging mirrors the analysis kernel: interior threads (window and outputs inside the arrays) share a
+// per-WARP cp.async ring -- every lane copies its own coefficient pair of each sub-band row (64-bit copies when
+// the rows are 8-byte aligned, else 2 x 32-bit), the last lane of a run adds the trailing pairs, D rows deep --
+// and read their window with 64-bit shared loads; only __syncwarp is needed.  Coefficient rows outside the
+// sub-band are zero-filled (periodization: wrapped).  The few border output columns run in separate CTAs, one
+// thread per output position.  A null `highs` means zeros (transform2d.py:137-139); out_h / out_w smaller than
+// the natural size crop.
+#include <algorithm>
 #include "dwt_levels.cuh"
 
 namespace b200w {
@@ -25,114 +32,159 @@ constexpr int sfb_n0_off(int L, bool per) { return sfb_a0_off(L, per) - sfb_off(
 constexpr int sfb_ks_off(int L, bool per) { return sfb_q0_off(L, per) - L / 2 + 1; }        // first needed coefficient
 constexpr int sfb_shift2(int L, bool per) { return ((sfb_ks_off(L, per) % 2) + 2) % 2; }    // pad down to even
 
-template <int V, int NCF>
-__device__ __forceinline__ void sfb_load_row(float (&c)[4][NCF], const float* lowp, long long low_rs, const float* hip,
-                                             size_t band, int kr, int h, int w, bool periodic, bool rows_in,
-                                             bool lane_in, int kb, const int (&cidx)[NCF]) {
-    int sr = kr;
-    if (!rows_in) sr = coef_index(kr, h, periodic);
-    if (sr < 0) {
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-#pragma unroll
-            for (int e = 0; e < NCF; ++e) c[b][e] = 0.f;
-        return;
-    }
-    const float* lp = lowp + (long long)sr * low_rs;
-    const float* hp = hip ? hip + (size_t)sr * w : nullptr;
-    if (lane_in) {
-        if (V == 2) {
-            const float2* q = reinterpret_cast<const float2*>(lp + kb);
-#pragma unroll
-            for (int i = 0; i < NCF / 2; ++i) { const float2 t = q[i]; c[0][2 * i] = t.x; c[0][2 * i + 1] = t.y; }
-        } else {
-#pragma unroll
-            for (int e = 0; e < NCF; ++e) c[0][e] = lp[kb + e];
-        }
-        if (hp) {
-#pragma unroll
-            for (int b = 1; b < 4; ++b) {
-                const float* src = hp + (size_t)(b - 1) * band + kb;
-                if (V == 2) {
-                    const float2* q = reinterpret_cast<const float2*>(src);
-#pragma unroll
-                    for (int i = 0; i < NCF / 2; ++i) { const float2 t = q[i]; c[b][2 * i] = t.x; c[b][2 * i + 1] = t.y; }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < NCF; ++e) c[b][e] = src[e];
-                }
-            }
-        }
-    } else {
-#pragma unroll
-        for (int e = 0; e < NCF; ++e) c[0][e] = cidx[e] >= 0 ? lp[cidx[e]] : 0.f;
-        if (hp) {
-#pragma unroll
-            for (int b = 1; b < 4; ++b)
-#pragma unroll
-                for (int e = 0; e < NCF; ++e) c[b][e] = cidx[e] >= 0 ? hp[(size_t)(b - 1) * band + cidx[e]] : 0.f;
-        }
-    }
-    if (!hp) {
-#pragma unroll
-        for (int b = 1; b < 4; ++b)
-#pragma unroll
-            for (int e = 0; e < NCF; ++e) c[b][e] = 0.f;
+constexpr int kSfbMaxRuns = 5;
+constexpr int kSfbMinThreads = 8;   // interior threads per row needed for the ring path (=> at most kSfbMaxRuns runs)
+
+template <int L, int S2>
+struct SfbStreamCfg {
+    static constexpr int H2 = L / 2;
+    static constexpr int NCF = 2 * ((S2 + H2 + 2) / 2);   // coefficients per window (even)
+    static constexpr int NS = NCF / 2;                    // float2 slots per window
+    static constexpr int RPB = 32 + kSfbMaxRuns * (NS - 1);   // float2 slots per band row of the ring
+    static constexpr int STAGE = 4 * RPB;                 // float2 per stage (one coefficient row, four bands)
+    static constexpr int D = L <= 8 ? 8 : 6;              // ring depth (coefficient rows)
+    static constexpr size_t smem = sizeof(float2) * (size_t)(kStreamNT / 32) * D * STAGE;
+    static constexpr int MINB = L <= 8 ? 5 : (L <= 12 ? 4 : 3);
+};
+template <int L>
+struct SfbSmem {   // one launch may mix 64-bit and 32-bit staged levels: size the ring for the larger window
+    static constexpr size_t a = SfbStreamCfg<L, sfb_shift2(L, false)>::smem;
+    static constexpr size_t b = SfbStreamCfg<L, sfb_shift2(L, true)>::smem;
+    static constexpr size_t c = SfbStreamCfg<L, 0>::smem;
+    static constexpr size_t value = a > b ? (a > c ? a : c) : (b > c ? b : c);
+};
+
+// source row of coefficient row kr: itself inside the sub-band, else zero (-1) or the periodic wrap
+__device__ __forceinline__ int sfb_src_row(int kr, int h, int periodic) {
+    if ((unsigned)kr < (unsigned)h) return kr;
+    return periodic ? coef_index_far(kr, h, periodic) : -1;
+}
+
+// block until every CTA item of the previous level of this plane has been published
+__device__ __forceinline__ void sfb_chain_wait(const unsigned* ctr, unsigned need) {
+    if (ctr != nullptr) {
+        if (threadIdx.x == 0)
+            while (ld_acquire_u32(ctr) < need) __nanosleep(20);
+        __syncthreads();
     }
 }
 
+// ---- interior threads: per-warp cp.async ring ----------------------------------------------------------
 template <int L, int V, int S2>
-__device__ __forceinline__ void sfb_stream_item(const SfbParams& p, const SfbLevel& lv, int plane, int it) {
-    constexpr int H2 = L / 2;
-    constexpr int NCF = V == 2 ? 2 * ((S2 + H2 + 2) / 2) : H2 + 1;   // coefficients loaded per band and row
-    constexpr int U = (H2 % 2) ? 2 * H2 : H2;                        // lcm(2, H2)
-
-    const int seg = it / lv.nt;
-    const int t = it - seg * lv.nt;
+__device__ __forceinline__ void sfb_ring_cta(const SfbParams& p, const SfbLevel& lv, int plane, int cta, float2* ring_all,
+                                             const unsigned* wait_ctr, unsigned wait_need) {
+    using C = SfbStreamCfg<L, S2>;
+    constexpr int H2 = C::H2, NCF = C::NCF, NS = C::NS, D = C::D;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int it = cta * kStreamNT + tid;
+    const bool active = it < lv.itemsA;
+    const int ntA = lv.ntA;
+    const int itc = active ? it : lv.itemsA - 1;     // inactive lanes shadow the last item (no copies, no stores)
+    const int seg = itc / ntA;
+    const int tl = itc - seg * ntA;
+    const int t = lv.tA0 + tl;
     const int m0 = lv.m_lo + seg * lv.Rp;                            // first output row pair (A-space)
     const int m_end = ((lv.offH + lv.out_h - 1) >> 1) + 1;
     const int nm = min(lv.Rp, m_end - m0);
-    const int nrows = nm + H2 - 1;                                   // coefficient rows feeding them
+    const int nrows = active ? nm + H2 - 1 : 0;                      // coefficient rows feeding them
     const int kr0 = m0 - (H2 - 1);
-    const int h = lv.h, w = lv.w;
-    const bool periodic = p.periodic != 0;
-    const bool rows_in = kr0 >= 0 && kr0 + nrows <= h;
-    const int kb = 2 * t + lv.kb_off;                                // first loaded coefficient column
-    const bool lane_in = kb >= 0 && kb + NCF <= w;
-    int cidx[NCF];
-#pragma unroll
-    for (int e = 0; e < NCF; ++e) cidx[e] = 0;
-    if (!lane_in) {
-#pragma unroll
-        for (int e = 0; e < NCF; ++e) cidx[e] = coef_index(kb + e, w, periodic);
-    }
+    const int h = lv.h, w = lv.w, periodic = p.periodic;
+    const int kb = 2 * t + lv.kb_off;                                // first staged coefficient column (>= 0)
+    const int seg_first = __shfl_sync(0xffffffffu, seg, 0);
+    const int slot = lane + (NS - 1) * (seg - seg_first);
+    const bool run_last = NS > 1 && active && (lane == 31 || tl == ntA - 1);
     const size_t band = (size_t)h * w;
-    const float* lowp = lv.low + (long long)plane * lv.low_ps;
     const long long low_rs = lv.low_rs;
-    const float* hip = lv.highs ? lv.highs + (size_t)plane * 3 * band : nullptr;
+    const float* lowcol = lv.low + (long long)plane * lv.low_ps + kb;
+    const bool has_hi = lv.highs != nullptr;
+    const float* hicol = has_hi ? lv.highs + (size_t)plane * 3 * band + kb : lowcol;
+    float2* ring = ring_all + (size_t)(tid >> 5) * D * C::STAGE;
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring) + (unsigned)slot * 8u;
 
-    const int out_h = lv.out_h, out_w = lv.out_w;
-    const int n0 = 4 * t + lv.n0_off;                                // first output column
+    // stage coefficient row q of this lane's segment into ring stage `st`.  Rows inside the sub-band take the
+    // plain cp.async (the zero-filling form costs three padding instructions each); zero rows and a missing
+    // `highs` are cleared with shared stores.
+    auto issue = [&](int q, int st) {
+        // nothing is staged beyond this lane's segment: the lanes that would read those slots (same run, same
+        // segment) are past their last row too, and an idle lane must not touch slots that belong to others
+        if (q < nrows) {
+            const int sr = sfb_src_row(kr0 + q, h, periodic);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const unsigned dst = ring_s + (unsigned)((st * 4 + b) * C::RPB) * 8u;
+                if (sr >= 0 && (b == 0 || has_hi)) {
+                    const float* src = b == 0 ? lowcol + (long long)sr * low_rs : hicol + (size_t)(b - 1) * band + (size_t)sr * w;
+                    if (V == 2) {
+                        cp_async<2>(dst, src);
+                        if (run_last) {
+#pragma unroll
+                            for (int k = 1; k < NS; ++k) cp_async<2>(dst + 8u * k, src + 2 * k);
+                        }
+                    } else {
+                        cp_async<1>(dst, src);
+                        cp_async<1>(dst + 4u, src + 1);
+                        if (run_last) {
+#pragma unroll
+                            for (int k = 2; k < NCF; ++k) cp_async<1>(dst + 4u * k, src + k);
+                        }
+                    }
+                } else {
+                    float2* d = ring + (st * 4 + b) * C::RPB + slot;
+                    d[0] = make_float2(0.f, 0.f);
+                    if (run_last) {
+#pragma unroll
+                        for (int k = 1; k < NS; ++k) d[k] = make_float2(0.f, 0.f);
+                    }
+                }
+            }
+        }
+    };
+
+    const int out_h = lv.out_h;
+    const int n0 = 4 * t + lv.n0_off;                                // first output column (all four are valid)
     const long long y_rs = lv.y_rs;
     int nrow = 2 * m0 - lv.offH;                                     // output row of the even row of pair m0
     float* yq = lv.y + (long long)plane * lv.y_ps + (long long)nrow * y_rs + n0;   // dereferenced only where valid
-    const bool full4 = n0 >= 0 && n0 + 3 < out_w;
-    const int yv = full4 ? lv.y_vec : 1;
+    const int yv = lv.y_vec;
 
-    float c[2][4][NCF];   // [double buffer][LL, LH, HL, HH][window element]
-    float acc[H2][8];     // ring of pending output row pairs: even row x4 columns, odd row x4 columns
-    sfb_load_row<V, NCF>(c[0], lowp, low_rs, hip, band, kr0, h, w, periodic, rows_in, lane_in, kb, cidx);
-
-    for (int qb = 0; qb < nrows; qb += U) {
+    // warp-uniform trip count (lanes of a warp may sit in segments of different length)
+    int npw = nrows;
 #pragma unroll
-        for (int uq = 0; uq < U; ++uq) {
-            const int q = qb + uq;
-            if (q < nrows) {
-                const int cur = uq & 1;
-                const int ph = uq % H2;
-                if (q + 1 < nrows)
-                    sfb_load_row<V, NCF>(c[cur ^ 1], lowp, low_rs, hip, band, kr0 + q + 1, h, w, periodic, rows_in,
-                                         lane_in, kb, cidx);
+    for (int o = 16; o > 0; o >>= 1) npw = max(npw, __shfl_xor_sync(0xffffffffu, npw, o));
+
+    sfb_chain_wait(wait_ctr, wait_need);
+#pragma unroll 1
+    for (int s = 0; s < D - 1; ++s) {
+        issue(s, s);
+        cp_async_commit();
+    }
+    float acc[H2][8];     // ring of pending output row pairs: even row x4 columns, odd row x4 columns
+    int st_r = 0, st_w = D - 1;
+    // long filters keep the accumulator ring in age order and shift it after each store instead of unrolling by
+    // L/2 (the unrolled body would not fit the instruction cache)
+    constexpr bool kRotate = L >= 10;
+    constexpr int UQ = kRotate ? 1 : H2;
+    for (int qb = 0; qb < npw; qb += UQ) {
+#pragma unroll
+        for (int ph = 0; ph < UQ; ++ph) {
+            const int q = qb + ph;
+            if (q < npw) {   // warp-uniform
+                cp_async_wait<D - 2>();   // this lane's copies of row q have landed ...
+                __syncwarp();             // ... and everybody's; all lanes are done reading row q-1
+                issue(q + D - 1, st_w);   // refill the stage row q-1 was read from
+                cp_async_commit();
+                st_w = st_w + 1 == D ? 0 : st_w + 1;
+                float c[4][NCF];
+                const float2* src = ring + (st_r * 4) * C::RPB + slot;
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) {
+                        const float2 v = src[b * C::RPB + k];
+                        c[b][2 * k] = v.x;
+                        c[b][2 * k + 1] = v.y;
+                    }
                 // W synthesis of this coefficient row: lo = h_lo branch (LL, HL), hi = h_hi branch (LH, HH)
                 float lo[4], hi[4];
 #pragma unroll
@@ -142,10 +194,10 @@ __device__ __forceinline__ void sfb_stream_item(const SfbParams& p, const SfbLev
 #pragma unroll
                     for (int u = 0; u < H2; ++u) {
                         const int kl = S2 + qo + H2 - 1 - u;
-                        a = fmaf(c[cur][0][kl], p.t.w_lo[par + 2 * u], a);
-                        a = fmaf(c[cur][2][kl], p.t.w_hi[par + 2 * u], a);
-                        b = fmaf(c[cur][1][kl], p.t.w_lo[par + 2 * u], b);
-                        b = fmaf(c[cur][3][kl], p.t.w_hi[par + 2 * u], b);
+                        a = fmaf(c[0][kl], p.t.w_lo[par + 2 * u], a);
+                        a = fmaf(c[2][kl], p.t.w_hi[par + 2 * u], a);
+                        b = fmaf(c[1][kl], p.t.w_lo[par + 2 * u], b);
+                        b = fmaf(c[3][kl], p.t.w_hi[par + 2 * u], b);
                     }
                     lo[e] = a;
                     hi[e] = b;
@@ -153,10 +205,10 @@ __device__ __forceinline__ void sfb_stream_item(const SfbParams& p, const SfbLev
                 // H synthesis: coefficient row q carries taps (2u, 2u+1) of output row pair q - (H2-1) + u
 #pragma unroll
                 for (int u = H2 - 1; u >= 0; --u) {
-                    const int slot = (ph + u + 1) % H2;
+                    const int sl = kRotate ? u : (ph + u + 1) % H2;
                     const float a0 = p.t.h_lo[2 * u], b0 = p.t.h_hi[2 * u];
                     const float a1 = p.t.h_lo[2 * u + 1], b1 = p.t.h_hi[2 * u + 1];
-                    float* s = acc[slot];
+                    float* s = acc[sl];
                     if (u == H2 - 1) {   // first contribution to that pair
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
@@ -177,8 +229,8 @@ __device__ __forceinline__ void sfb_stream_item(const SfbParams& p, const SfbLev
                     }
                 }
                 // pair q - (H2-1) is complete
-                if (q >= H2 - 1) {
-                    const float* s = acc[(ph + 1) % H2];
+                if (q >= H2 - 1 && q < nrows) {
+                    const float* s = acc[kRotate ? 0 : (ph + 1) % H2];
 #pragma unroll
                     for (int r = 0; r < 2; ++r) {
                         const int row = nrow + r;
@@ -190,26 +242,101 @@ __device__ __forceinline__ void sfb_stream_item(const SfbParams& p, const SfbLev
                                 *reinterpret_cast<float2*>(d) = make_float2(s[4 * r], s[4 * r + 1]);
                                 *reinterpret_cast<float2*>(d + 2) = make_float2(s[4 * r + 2], s[4 * r + 3]);
                             } else {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e)
-                                    if (n0 + e >= 0 && n0 + e < out_w) d[e] = s[4 * r + e];
+                                d[0] = s[4 * r]; d[1] = s[4 * r + 1]; d[2] = s[4 * r + 2]; d[3] = s[4 * r + 3];
                             }
                         }
                     }
                     nrow += 2;
                     yq += 2 * y_rs;
                 }
+                if (kRotate) {
+#pragma unroll
+                    for (int k = 0; k + 1 < H2; ++k)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[k][i] = acc[k + 1][i];
+                }
+                st_r = st_r + 1 == D ? 0 : st_r + 1;
             }
         }
     }
+    cp_async_wait<0>();
 }
 
-template <int L, int V, int S2>
-__global__ void __launch_bounds__(kStreamNT) sfb_stream_kernel(const __grid_constant__ SfbParams p) {
+// ---- border output columns: one thread per output position ---------------------------------------------
+// All (L/2)^2 x 4 coefficients of an output are loaded before any arithmetic (clamped address + select), so the
+// thread pays one memory round trip; rows are done in chunks to bound the registers.
+template <int L>
+__device__ __forceinline__ void sfb_border_item(const SfbParams& p, const SfbLevel& lv, int plane, int it) {
+    constexpr int H2 = L / 2;
+    const int ncB = lv.nA0 + lv.out_w - lv.nA1;      // border columns per output row
+    const int nH = it / ncB;
+    const int e0 = it - nH * ncB;
+    const int nW = e0 < lv.nA0 ? e0 : e0 - lv.nA0 + lv.nA1;
+    const int h = lv.h, w = lv.w, periodic = p.periodic;
+    const size_t band = (size_t)h * w;
+    const float* lowp = lv.low + (long long)plane * lv.low_ps;
+    const bool has_hi = lv.highs != nullptr;
+    const float* hip = has_hi ? lv.highs + (size_t)plane * 3 * band : lowp;
+    const int AH = nH + lv.offH, AW = nW + lv.offW;
+    const int parH = AH & 1, parW = AW & 1;
+    int kc[H2];
+#pragma unroll
+    for (int u = 0; u < H2; ++u) {
+        const int k = (AW >> 1) - u;
+        kc[u] = (unsigned)k < (unsigned)w ? k : (periodic ? coef_index_far(k, w, periodic) : -1);
+    }
+    float y = 0.f;
+    constexpr int CH = H2 < 3 ? H2 : 3;
+#pragma unroll
+    for (int u0 = 0; u0 < H2; u0 += CH) {
+        float v[CH][4][H2];
+        bool rok[CH];
+#pragma unroll
+        for (int uu = 0; uu < CH; ++uu) {
+            const int uH = u0 + uu;
+            const int kr = uH < H2 ? sfb_src_row((AH >> 1) - uH, h, periodic) : -1;
+            rok[uu] = kr >= 0;
+            const int row = max(kr, 0);
+            const float* lp = lowp + (long long)row * lv.low_rs;
+            const float* hp = hip + (size_t)row * w;
+#pragma unroll
+            for (int u = 0; u < H2; ++u) {
+                const int col = max(kc[u], 0);
+                v[uu][0][u] = lp[col];
+                v[uu][1][u] = has_hi ? hp[col] : 0.f;
+                v[uu][2][u] = has_hi ? hp[band + col] : 0.f;
+                v[uu][3][u] = has_hi ? hp[2 * band + col] : 0.f;
+            }
+        }
+#pragma unroll
+        for (int uu = 0; uu < CH; ++uu) {
+            const int uH = u0 + uu;
+            if (uH < H2) {
+                float lo = 0.f, hi = 0.f;   // W-synthesised values to be combined with h_lo / h_hi
+#pragma unroll
+                for (int u = 0; u < H2; ++u) {
+                    const bool ok = rok[uu] && kc[u] >= 0;
+                    const float gl = p.t.w_lo[parW + 2 * u], gh = p.t.w_hi[parW + 2 * u];
+                    lo = fmaf(ok ? v[uu][0][u] : 0.f, gl, lo);    // LL
+                    hi = fmaf(ok ? v[uu][1][u] : 0.f, gl, hi);    // LH
+                    lo = fmaf(ok ? v[uu][2][u] : 0.f, gh, lo);    // HL
+                    hi = fmaf(ok ? v[uu][3][u] : 0.f, gh, hi);    // HH
+                }
+                y = fmaf(lo, p.t.h_lo[parH + 2 * uH], y);
+                y = fmaf(hi, p.t.h_hi[parH + 2 * uH], y);
+            }
+        }
+    }
+    lv.y[(long long)plane * lv.y_ps + (long long)nH * lv.y_rs + nW] = y;
+}
+
+template <int L, int S2V>
+__global__ void __launch_bounds__(kStreamNT, SfbStreamCfg<L, S2V>::MINB) sfb_stream_kernel(const __grid_constant__ SfbParams p) {
+    extern __shared__ float2 sfb_ring_all[];
     __shared__ unsigned s_item;
     const int tid = threadIdx.x;
     unsigned item = blockIdx.x;
-    if (p.J > 1) {
+    if (p.J > 1) {   // work items are handed out in list order: an item only waits for earlier, running ones
         if (tid == 0) s_item = atomicAdd(p.ticket, 1u);
         __syncthreads();
         item = s_item;
@@ -220,30 +347,33 @@ __global__ void __launch_bounds__(kStreamNT) sfb_stream_kernel(const __grid_cons
     const SfbLevel& lv = p.lv[level];
     const unsigned local = item - (unsigned)lv.cta_base;
     const int plane = (int)(local / (unsigned)lv.cpp);
-    const int c = (int)(local - (unsigned)plane * (unsigned)lv.cpp);
-    if (level > 0) {
-        if (tid == 0) {
-            const unsigned need = (unsigned)p.lv[level - 1].cpp;
-            const unsigned* ctr = p.done + (size_t)(level - 1) * p.planes + plane;
-            while (ld_acquire_u32(ctr) < need) __nanosleep(100);
-        }
-        __syncthreads();
+    const int cta = (int)(local - (unsigned)plane * (unsigned)lv.cpp);
+    // the previous (coarser) level of this plane must be complete before its output is read as `low`
+    const unsigned* wait_ctr = level > 0 ? p.done + (size_t)(level - 1) * p.planes + plane : nullptr;
+    const unsigned wait_need = level > 0 ? (unsigned)p.lv[level - 1].cpp : 0u;
+    if (cta < lv.cppA) {
+        if (lv.vec2) sfb_ring_cta<L, 2, S2V>(p, lv, plane, cta, sfb_ring_all, wait_ctr, wait_need);
+        else sfb_ring_cta<L, 1, 0>(p, lv, plane, cta, sfb_ring_all, wait_ctr, wait_need);
+    } else {
+        sfb_chain_wait(wait_ctr, wait_need);
+        const int it = (cta - lv.cppA) * kStreamNT + tid;
+        if (it < lv.itemsB) sfb_border_item<L>(p, lv, plane, it);
     }
-    const int it = c * kStreamNT + tid;
-    if (it < lv.items) sfb_stream_item<L, V, S2>(p, lv, plane, it);
     if (level + 1 < p.J) {
         __syncthreads();
         if (tid == 0) signal_done(p.done + (size_t)level * p.planes + plane);
     }
 }
 
+static int sfb_env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    if (!e || !*e) return dflt;
+    const int v = atoi(e);
+    return v > 0 ? v : dflt;
+}
 static int stream_pairs_override() {
     static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("B200W_STREAM_ROWS");
-        v = e ? atoi(e) : 0;
-        if (v < 0) v = 0;
-    }
+    if (v < 0) v = sfb_env_int("B200W_STREAM_ROWS", 0);
     return v;
 }
 
@@ -255,42 +385,50 @@ bool sfb_stream_supported(const SfbParams& p, int L) {
     return true;
 }
 
-// can every level read its coefficient rows with 64-bit loads?
-static bool sfb_rows_vec2(const SfbParams& p) {
-    for (int j = 0; j < p.J; ++j) {
-        const SfbLevel& lv = p.lv[j];
-        if ((lv.low_rs & 1) || (lv.low_ps & 1) || !aligned_to(lv.low, 8)) return false;
-        if (lv.highs && ((lv.w & 1) || !aligned_to(lv.highs, 8))) return false;
-    }
-    return true;
-}
-
-template <int L, int V, int S2>
+template <int L, bool PER>
 static int launch_sfb_stream_t(SfbParams& p, int sms, cudaStream_t st) {
     constexpr int H2 = L / 2;
-    const bool per = p.periodic != 0;
-    const long long target = (long long)sms * 32 * 12;
-    const int rmin = H2 > 1 ? 4 * (H2 - 1) : 4;
+    constexpr int S2V = sfb_shift2(L, PER);
+    using CV = SfbStreamCfg<L, S2V>;
+    using C1 = SfbStreamCfg<L, 0>;
+    // segments of ~16 output row pairs (see the analysis launcher for the rationale); the dependent levels of a
+    // chain -- every level but the last, finest one -- shrink until they fill the resident CTA slots
+    const int rpref = std::max(16, 4 * (H2 - 1));
+    const long long slots = (long long)sms * CV::MINB;
     long long base = 0;
     for (int j = 0; j < p.J; ++j) {
         SfbLevel& lv = p.lv[j];
-        lv.q0_off = per ? sfb_q0_off(L, true) : sfb_q0_off(L, false);
-        lv.n0_off = per ? sfb_n0_off(L, true) : sfb_n0_off(L, false);
-        const int ks_off = per ? sfb_ks_off(L, true) : sfb_ks_off(L, false);
-        lv.kb_off = V == 2 ? ks_off - S2 : ks_off;
+        lv.vec2 = (!(lv.low_rs & 1) && !(lv.low_ps & 1) && aligned_to(lv.low, 8) &&
+                   (!lv.highs || (!(lv.w & 1) && aligned_to(lv.highs, 8)))) ? 1 : 0;
+        const int ncf = lv.vec2 ? CV::NCF : C1::NCF;
+        lv.n0_off = sfb_n0_off(L, PER);
+        lv.kb_off = lv.vec2 ? sfb_ks_off(L, PER) - S2V : sfb_ks_off(L, PER);
         lv.m_lo = lv.offH >> 1;
-        lv.nt = ceil_div(lv.out_w - lv.n0_off, 4);
+        // interior threads: window [kb, kb+ncf) inside [0, w) and outputs n0 .. n0+3 inside [0, out_w)
+        int t0 = lv.kb_off < 0 ? (-lv.kb_off + 1) / 2 : 0;
+        if (lv.n0_off < 0 && t0 < 1) t0 = 1;
+        int t1 = lv.w - ncf - lv.kb_off >= 0 ? (lv.w - ncf - lv.kb_off) / 2 + 1 : 0;
+        const int t1o = lv.out_w - 4 - lv.n0_off >= 0 ? (lv.out_w - 4 - lv.n0_off) / 4 + 1 : 0;
+        t1 = std::min(t1, t1o);
+        lv.tA0 = t0;
+        lv.ntA = t1 - t0;
+        if (lv.ntA < kSfbMinThreads) lv.ntA = 0;   // too narrow for the ring: every column takes the border path
+        lv.nA0 = lv.ntA > 0 ? 4 * lv.tA0 + lv.n0_off : lv.out_w;
+        lv.nA1 = lv.ntA > 0 ? 4 * (lv.tA0 + lv.ntA) + lv.n0_off : lv.out_w;
         const int npairs = ((lv.offH + lv.out_h - 1) >> 1) + 1 - lv.m_lo;
-        const long long rowitems = (long long)p.planes * lv.nt;
-        long long nseg_want = (target + rowitems - 1) / rowitems;
-        if (nseg_want < 1) nseg_want = 1;
-        int Rp = (int)((npairs + nseg_want - 1) / nseg_want);
-        if (Rp < rmin) Rp = rmin;
+        int Rp = rpref;
+        if (j + 1 < p.J) {
+            const int rmin = std::max(2, H2 - 1);
+            while (Rp > rmin && (long long)p.planes * ceil_div(ceil_div(npairs, Rp) * std::max(lv.ntA, 1), kStreamNT) < slots)
+                Rp = std::max(rmin, Rp - 2);
+        }
         if (stream_pairs_override() > 0) Rp = stream_pairs_override();
         if (Rp > npairs) Rp = npairs;
         lv.Rp = Rp;
-        lv.items = ceil_div(npairs, Rp) * lv.nt;
-        lv.cpp = ceil_div(lv.items, kStreamNT);
+        lv.itemsA = ceil_div(npairs, Rp) * lv.ntA;
+        lv.cppA = ceil_div(lv.itemsA, kStreamNT);
+        lv.itemsB = lv.out_h * (lv.nA0 + lv.out_w - lv.nA1);
+        lv.cpp = lv.cppA + ceil_div(lv.itemsB, kStreamNT);
         lv.y_vec = 1;
         if (lv.n0_off == 0 && !(lv.y_rs & 1) && !(lv.y_ps & 1) && aligned_to(lv.y, 8)) lv.y_vec = 2;
         if (lv.y_vec == 2 && !(lv.y_rs & 3) && !(lv.y_ps & 3) && aligned_to(lv.y, 16)) lv.y_vec = 4;
@@ -303,17 +441,15 @@ static int launch_sfb_stream_t(SfbParams& p, int sms, cudaStream_t st) {
         const int rc = zero_sync_words(p.ticket, (size_t)p.J * p.planes + 1, st);
         if (rc) return rc;
     }
-    sfb_stream_kernel<L, V, S2><<<(unsigned)base, kStreamNT, 0, st>>>(p);
+    sfb_stream_kernel<L, S2V><<<(unsigned)base, kStreamNT, SfbSmem<L>::value, st>>>(p);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? B200W_OK : set_last_cuda_error(e);
 }
 
 template <int L>
 static int launch_sfb_stream_l(SfbParams& p, int sms, cudaStream_t st) {
-    const bool v2 = sfb_rows_vec2(p);
-    if (!v2) return launch_sfb_stream_t<L, 1, 0>(p, sms, st);
-    if (p.periodic) return launch_sfb_stream_t<L, 2, sfb_shift2(L, true)>(p, sms, st);
-    return launch_sfb_stream_t<L, 2, sfb_shift2(L, false)>(p, sms, st);
+    if (p.periodic) return launch_sfb_stream_t<L, true>(p, sms, st);
+    return launch_sfb_stream_t<L, false>(p, sms, st);
 }
 
 int launch_sfb_stream(SfbParams& p, int L, int sms, cudaStream_t st) {
