@@ -6,6 +6,7 @@ Drop-in surface (same names and signatures as the reference):
 * ``DWTForward``, ``DWTInverse`` and the aliases ``DWT``, ``IDWT``, ``DWT2D``, ``IDWT2D``
   (``pytorch_wavelets/__init__.py:24-33``), ``dwt.lowlevel.AFB2D`` / ``SFB2D`` / ``afb2d`` / ``sfb2d``
 * ``SSIM``, ``ssim`` (``ssim.py``)
+* ``HostPipeline``: host-buffer front end (chunked, stream-overlapped H2D | kernels | D2H)
 
 Everything computes in hand-written CUDA kernels behind ``torch.ops.b200wave``;
 there is no CPU path.
@@ -16,6 +17,7 @@ from .dwt import lowlevel  # noqa: F401
 from .dwt.transform2d import DWTForward, DWTInverse
 from .ssim import SSIM, ssim
 from .wavelets import Wavelet, wavelist  # noqa: F401
+from .hostpipe import HostPipeline
 
 __version__ = "0.1.0"
 
@@ -25,4 +27,4 @@ DWT2D = DWT
 IDWT2D = IDWT
 
 __all__ = ["DWTForward", "DWTInverse", "DWT", "IDWT", "DWT2D", "IDWT2D", "SSIM", "ssim", "lowlevel",
-           "Wavelet", "wavelist", "__version__"]
+           "Wavelet", "wavelist", "HostPipeline", "__version__"]

@@ -423,6 +423,9 @@ static int launch_afb_stream_t(AfbParams& p, int sms, cudaStream_t st) {
         if (cpR > lv.Wo / 2) cpR = lv.Wo / 2;
         lv.ncpA = cpR - lv.cp0A;
         if (lv.ncpA < kMinColPairs) lv.ncpA = 0;              // too narrow for the ring: all columns take the border path
+        // experiment knob: route small dependent levels through the one-thread-per-output path (measured slower:
+        // profiles/r01_notes.md), off by default
+        if (j > 0 && (long long)lv.Ho * lv.Wo <= env_int("B200W_DIRECT_MAX", 0)) lv.ncpA = 0;
         // level 0 keeps the preferred length (measured best even when it leaves CTA slots empty); the dependent
         // levels of a chain shrink until they fill the slots
         int R = rpref;
