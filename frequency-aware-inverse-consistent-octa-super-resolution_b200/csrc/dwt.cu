@@ -648,6 +648,15 @@ static bool force_tiled() {
     if (v < 0) v = env_flag("B200W_FORCE_TILED");
     return v == 1;
 }
+// B200W_PLANE=1: run the levels whose planes fit in shared memory with the plane-resident kernels (dwt_plane.cu).
+// Off by default: as measured in round 1 (profiles/r01_notes.md) they are instruction-bound and only match the
+// chain kernels; they stay in the tree as a third, independently written implementation that the parity tests
+// cross-check, and as the starting point for fusing the small levels.
+static bool no_plane() {
+    static int v = -1;
+    if (v < 0) v = env_flag("B200W_PLANE");
+    return v != 1;
+}
 
 static bool mode_supported(int mode) {
     return mode == B200W_MODE_ZERO || mode == B200W_MODE_SYMMETRIC || mode == B200W_MODE_PERIODIZATION ||
@@ -815,6 +824,20 @@ static bool templated_taps(int Lw, int Lh) {
 }
 
 // ---- analysis chain --------------------------------------------------------------------------------
+static int run_afb_big_levels(AfbParams& p, int L, cudaStream_t st) {
+    if (!force_tiled() && afb_stream_supported(p, L)) return launch_afb_stream(p, L, device_info().sms, st);
+    switch (L) {
+        case 2: return launch_afb_chain<2>(p, st);
+        case 4: return launch_afb_chain<4>(p, st);
+        case 6: return launch_afb_chain<6>(p, st);
+        case 8: return launch_afb_chain<8>(p, st);
+        case 10: return launch_afb_chain<10>(p, st);
+        case 12: return launch_afb_chain<12>(p, st);
+        case 14: return launch_afb_chain<14>(p, st);
+        default: return launch_afb_chain<16>(p, st);
+    }
+}
+
 // level sizes of the analysis chain; returns a status
 static int afb_dims(int H, int W, int Lw, int Lh, int mode, int J, const int* pad_hw, int* Ho, int* Wo) {
     int h = H, w = W;
@@ -909,17 +932,19 @@ static int run_afb_chain(const float* x, int64_t x_ps, int64_t x_rs, int planes,
         w = lv.Wo;
     }
     if (templated_taps(Lw, Lh)) {
-        if (!force_tiled() && afb_stream_supported(p, Lw)) return launch_afb_stream(p, Lw, device_info().sms, st);
-        switch (Lw) {
-            case 2: return launch_afb_chain<2>(p, st);
-            case 4: return launch_afb_chain<4>(p, st);
-            case 6: return launch_afb_chain<6>(p, st);
-            case 8: return launch_afb_chain<8>(p, st);
-            case 10: return launch_afb_chain<10>(p, st);
-            case 12: return launch_afb_chain<12>(p, st);
-            case 14: return launch_afb_chain<14>(p, st);
-            default: return launch_afb_chain<16>(p, st);
+        // levels whose input plane fits in shared memory run plane-resident (one launch for all of them); the
+        // bigger levels before them go through the stream chain (or the tile chain when rows are unaligned)
+        int first = (force_tiled() || no_plane()) ? J : afb_plane_first(p, Lw);
+        if (first < J) {
+            if (first > 0) {
+                AfbParams head = p;
+                head.J = first;
+                rc = run_afb_big_levels(head, Lw, st);
+                if (rc) return rc;
+            }
+            return launch_afb_plane(p, Lw, first, st);
         }
+        return run_afb_big_levels(p, Lw, st);
     }
     for (int j = 0; j < J; ++j) {  // level by level with the direct kernel
         AfbDirectParams d;
@@ -937,6 +962,20 @@ static int run_afb_chain(const float* x, int64_t x_ps, int64_t x_rs, int planes,
 }
 
 // ---- synthesis chain -------------------------------------------------------------------------------
+static int run_sfb_big_levels(SfbParams& p, int L, cudaStream_t st) {
+    if (!force_tiled() && sfb_stream_supported(p, L)) return launch_sfb_stream(p, L, device_info().sms, st);
+    switch (L) {
+        case 2: return launch_sfb_chain<2>(p, st);
+        case 4: return launch_sfb_chain<4>(p, st);
+        case 6: return launch_sfb_chain<6>(p, st);
+        case 8: return launch_sfb_chain<8>(p, st);
+        case 10: return launch_sfb_chain<10>(p, st);
+        case 12: return launch_sfb_chain<12>(p, st);
+        case 14: return launch_sfb_chain<14>(p, st);
+        default: return launch_sfb_chain<16>(p, st);
+    }
+}
+
 static int sfb_check_dims(int planes, const int* hs, const int* ws, int Lw, int Lh, int mode, int J, const int* out_hs,
                           const int* out_ws) {
     if (!mode_supported(mode)) return B200W_ERR_BAD_MODE;
@@ -1020,17 +1059,18 @@ static int run_sfb_chain(const float* yl, int64_t yl_ps, int64_t yl_rs, const fl
         lv.y_vec = 1;
     }
     if (templated_taps(Lw, Lh)) {
-        if (!force_tiled() && sfb_stream_supported(p, Lw)) return launch_sfb_stream(p, Lw, device_info().sms, st);
-        switch (Lw) {
-            case 2: return launch_sfb_chain<2>(p, st);
-            case 4: return launch_sfb_chain<4>(p, st);
-            case 6: return launch_sfb_chain<6>(p, st);
-            case 8: return launch_sfb_chain<8>(p, st);
-            case 10: return launch_sfb_chain<10>(p, st);
-            case 12: return launch_sfb_chain<12>(p, st);
-            case 14: return launch_sfb_chain<14>(p, st);
-            default: return launch_sfb_chain<16>(p, st);
+        // the coarse levels whose planes fit in shared memory run plane-resident (one launch), the finer ones after
+        // them through the stream chain (or the tile chain)
+        const int count = (force_tiled() || no_plane()) ? 0 : sfb_plane_count(p, Lw);
+        if (count > 0) {
+            rc = launch_sfb_plane(p, Lw, count, st);
+            if (rc || count == J) return rc;
+            SfbParams tail = p;
+            for (int c = count; c < J; ++c) tail.lv[c - count] = p.lv[c];
+            tail.J = J - count;
+            return run_sfb_big_levels(tail, Lw, st);
         }
+        return run_sfb_big_levels(p, Lw, st);
     }
     for (int c = 0; c < J; ++c) {
         SfbDirectParams d;

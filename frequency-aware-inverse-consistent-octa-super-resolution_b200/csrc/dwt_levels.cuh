@@ -107,6 +107,14 @@ int launch_afb_stream(AfbParams& p, int L, int sms, cudaStream_t st);
 bool sfb_stream_supported(const SfbParams& p, int L);
 int launch_sfb_stream(SfbParams& p, int L, int sms, cudaStream_t st);
 
+// plane-resident kernels (dwt_plane.cu): one CTA per plane runs the small levels of a transform in shared memory.
+// afb_plane_first = first analysis level from which on the rest fits (p.J = none); sfb_plane_count = number of
+// leading (coarse) synthesis chain positions that fit (0 = none).
+int afb_plane_first(const AfbParams& p, int L);
+int launch_afb_plane(const AfbParams& p, int L, int first, cudaStream_t st);
+int sfb_plane_count(const SfbParams& p, int L);
+int launch_sfb_plane(const SfbParams& p, int L, int count, cudaStream_t st);
+
 // clears the ticket + completion counters of a chain on the stream (a kernel rather than a memset node: inside a
 // CUDA graph a kernel -> memset -> kernel sequence costs several microseconds of engine switching)
 int zero_sync_words(unsigned* words, size_t n, cudaStream_t st);
