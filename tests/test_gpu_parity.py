@@ -86,6 +86,15 @@ def _wave_taps(name):
     ("bior2.4", 2, "periodization", (2, 2, 64, 64)),
     ("db1", 1, "reflect", (5, 1, 256, 256)),          # model.py:140 (haar/J=1/reflect on 256x256)
     ("db10", 1, "symmetric", (1, 1, 70, 90)),         # 20 taps: direct kernel
+    # 16-byte aligned rows: the streaming kernels (ring + border classes, several segments / warps per row)
+    ("db4", 2, "periodic", (2, 1, 128, 96)),
+    ("db8", 2, "symmetric", (1, 1, 160, 200)),        # 16 taps: shifting accumulator ring
+    ("db5", 3, "zero", (3, 1, 96, 160)),
+    ("db2", 3, "reflect", (2, 2, 200, 104)),
+    ("db1", 4, "zero", (2, 1, 128, 256)),
+    ("db6", 2, "periodization", (1, 1, 96, 128)),
+    ("db3", 2, "symmetric", (3, 1, 304, 304)),        # cfg2 geometry
+    ("db7", 2, "periodization", (1, 1, 256, 132)),
 ])
 def test_oracle_dwt_roundtrip_seeded(wave, J, mode, shape):
     rng = np.random.default_rng(hash((wave, J, mode)) % (2 ** 32))
@@ -359,3 +368,19 @@ def test_host_pipeline_matches_direct_call():
         assert rec.shape == rec_ref.shape and dx.shape == dx_ref.shape
         assert rel_err(rec, rec_ref.detach().cpu()) < 1e-6
         assert rel_err(dx, dx_ref.detach().cpu()) < 1e-6
+
+
+@pytest.mark.parametrize("env", ["B200W_FORCE_TILED", "B200W_PLANE", "B200W_FORCE_DIRECT"])
+def test_alternative_kernel_paths(env):
+    """The same golden / oracle cases through the other implementations of the path (the env switches are read
+    once per process, hence a child pytest): shared-memory tile kernels, plane-resident kernels, direct kernels."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    child_env = dict(os.environ)
+    child_env[env] = "1"
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-x",
+                          "-m", "gpu", "-k", "golden_dwt or golden_idwt or oracle_dwt_roundtrip or commutativity",
+                          "-p", "no:cacheprovider"],
+                         cwd=root, env=child_env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                         timeout=1500)
+    assert res.returncode == 0, res.stdout[-3000:]
