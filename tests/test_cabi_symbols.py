@@ -89,3 +89,42 @@ def test_argument_validation_happens_before_any_launch(lib):
         _cabi.check(_cabi.ERR_BAD_MODE, "constant")
     with pytest.raises(_cabi.B200WaveError):
         _cabi.check(_cabi.ERR_BAD_SHAPE)
+
+
+def test_multilevel_entry_points_validate_before_any_launch(lib):
+    """b200w_dwt2_f32 / b200w_idwt2_f32: workspace sizing is host arithmetic and bad arguments come back as status
+    codes without touching the (absent) GPU."""
+    t6, n6 = _cabi.taps_array([0.1] * 6)
+    bogus = ctypes.c_void_p(256)
+    # cfg2: 64 planes of 304x304, db3 (6 taps), symmetric, J=3 -> LL scratch of levels 0 and 1 + counters
+    ws3 = lib.b200w_dwt2_workspace_bytes(64, 304, 304, 6, 6, 1, 3, None)
+    ll0 = 64 * 154 * 156 * 4     # rows padded to a multiple of 4 floats
+    ll1 = 64 * 79 * 80 * 4
+    assert ws3 >= ll0 + ll1 and ws3 < ll0 + ll1 + 4096
+    assert lib.b200w_dwt2_workspace_bytes(64, 304, 304, 6, 6, 1, 1, None) == 0          # J == 1 needs none
+    assert lib.b200w_dwt2_workspace_bytes(64, 304, 304, 6, 6, 3, 3, None) == 0          # bad mode
+    pads = _cabi.int_array([0, 0, 1, 1, 0, 1])
+    assert lib.b200w_dwt2_workspace_bytes(64, 304, 304, 6, 6, 1, 3, pads) > ws3         # zero-extended levels
+    highs = _cabi.ptr_array([None, None, None])
+    highs[0] = highs[1] = highs[2] = 256
+    common = (bogus, 304 * 304, 304, 64, 304, 304, t6, t6, n6, t6, t6, n6)
+    assert lib.b200w_dwt2_f32(*common, 1, 3, None, bogus, highs, None, 0, None) == _cabi.ERR_WORKSPACE
+    assert lib.b200w_dwt2_f32(*common, 1, 3, None, bogus, highs, bogus, 16, None) == _cabi.ERR_WORKSPACE
+    assert lib.b200w_dwt2_f32(*common, 1, 9, None, bogus, highs, bogus, ws3, None) == _cabi.ERR_BAD_SHAPE
+    assert lib.b200w_dwt2_f32(*common, 5, 3, None, bogus, highs, bogus, ws3, None) == _cabi.ERR_BAD_MODE
+    assert lib.b200w_dwt2_f32(*common, 1, 3, None, None, highs, bogus, ws3, None) == _cabi.ERR_NULL_POINTER
+    bad_pads = _cabi.int_array([0, 0, 2, 0, 0, 0])
+    assert lib.b200w_dwt2_f32(*common, 1, 3, bad_pads, bogus, highs, bogus, ws3, None) == _cabi.ERR_BAD_SHAPE
+
+    hs, ws = _cabi.int_array([154, 79, 42]), _cabi.int_array([154, 79, 42])
+    ohs, ows = _cabi.int_array([304, 154, 80]), _cabi.int_array([304, 154, 80])
+    wsi = lib.b200w_idwt2_workspace_bytes(64, 3, ohs, ows)
+    assert wsi >= 64 * (154 * 156 + 80 * 80) * 4
+    assert lib.b200w_idwt2_workspace_bytes(64, 1, ohs, ows) == 0
+    syn = (bogus, 42 * 42, 42, highs, 64, hs, ws, t6, t6, n6, t6, t6, n6)
+    assert lib.b200w_idwt2_f32(*syn, 1, 3, ohs, ows, bogus, None, 0, None) == _cabi.ERR_WORKSPACE
+    too_big = _cabi.int_array([305, 154, 80])
+    assert lib.b200w_idwt2_f32(*syn, 1, 3, too_big, ows, bogus, bogus, wsi, None) == _cabi.ERR_BAD_SHAPE
+    small_prev = _cabi.int_array([304, 153, 80])    # level 0 needs a 154-row low-pass, level 1 only yields 153
+    assert lib.b200w_idwt2_f32(*syn, 1, 3, small_prev, ows, bogus, bogus, wsi, None) == _cabi.ERR_BAD_SHAPE
+    assert lib.b200w_idwt2_f32(*syn, 1, 3, ohs, ows, None, bogus, wsi, None) == _cabi.ERR_NULL_POINTER
