@@ -52,6 +52,16 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of that kernel on this workload, from the committed
+    `ncu --set full` capture (profiles/r01_traffic.json); None when there is no capture for it."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+            return json.load(fh).get(workload, {}).get(kernel)
+    except (OSError, ValueError):
+        return None
+
+
 def level_sizes(h, w, L, J, mode):
     out = []
     for _ in range(J):
@@ -421,10 +431,23 @@ def main():
                        for s in sets]
                 t_sfb = time_kernel(lambda i: lowlevel.SFB2D.apply(ll1[i % nsets][0], ll1[i % nsets][1], ifm.g0_col,
                                                                    ifm.g1_col, ifm.g0_row, ifm.g1_row, mode))
-                del coeffs
-                kernels = {"afb2d_level1": {"s": t_afb, "GB/s": lvl_bytes / t_afb / 1e9, "bytes": lvl_bytes},
-                           "sfb2d_level1": {"s": t_sfb, "GB/s": lvl_bytes / t_sfb / 1e9, "bytes": lvl_bytes}}
+                kernels = {"afb2d_level1": {"s": t_afb, "GB/s": lvl_bytes / t_afb / 1e9, "bytes": lvl_bytes,
+                                            "sass": "afb_stream_kernel"},
+                           "sfb2d_level1": {"s": t_sfb, "GB/s": lvl_bytes / t_sfb / 1e9, "bytes": lvl_bytes,
+                                            "sass": "sfb_stream_kernel"}}
                 name = "afb2d_level1" if t_afb >= t_sfb else "sfb2d_level1"
+                if cfg["J"] > 1:
+                    # the kernels the step actually launches: one chain kernel per J-level transform (forward and
+                    # backward passes use the same two kernels)
+                    chain_bytes = dwt_pass_bytes(cfg["shape"], L, cfg["J"], cfg["mode"])
+                    t_dwt = time_kernel(lambda i: xfm(sets[i % nsets][0].detach()))
+                    t_idwt = time_kernel(lambda i: ifm(coeffs[i % nsets]))
+                    kernels["dwt2_chain"] = {"s": t_dwt, "GB/s": chain_bytes / t_dwt / 1e9, "bytes": chain_bytes,
+                                             "sass": "afb_stream_kernel", "levels": cfg["J"]}
+                    kernels["idwt2_chain"] = {"s": t_idwt, "GB/s": chain_bytes / t_idwt / 1e9, "bytes": chain_bytes,
+                                              "sass": "sfb_stream_kernel", "levels": cfg["J"]}
+                    name = "dwt2_chain" if t_dwt >= t_idwt else "idwt2_chain"
+                del coeffs
             else:
                 from b200wave import ops
                 from b200wave.ssim import _win_taps
@@ -441,7 +464,7 @@ def main():
                 name = "ssim_fwd" if t_f >= t_b else "ssim_bwd"
         k = kernels[name]
         roof = {"bound": "hbm", "kernel": name, "achieved": k["GB/s"], "peak": peak, "unit": "GB/s",
-                "frac": k["GB/s"] / peak, "traffic": None, "peak_source": peak_src,
+                "frac": k["GB/s"] / peak, "traffic": ncu_traffic(args.workload, name), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": k["bytes"], "launch_us": k["s"] * 1e6,
                 "note": "timed alone: %d launches over rotating inputs > L2 in one CUDA graph, CUDA events" % reps}
     clocks = sampler.stop() if sampler else None

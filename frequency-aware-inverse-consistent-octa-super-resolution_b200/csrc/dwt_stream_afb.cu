@@ -22,6 +22,7 @@
 // column maps of the padding mode.
 // Segments overlap by L-2 input rows (re-read through L2).
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include "dwt_levels.cuh"
 
@@ -270,7 +271,9 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
 // latency instead of a dependent march), at the price of recomputing the row pass L/2 times -- for < 3 % of
 // the outputs.
 template <int L, int S>
-__device__ __forceinline__ void afb_border_item(const AfbParams& p, const AfbLevel& lv, int plane, int it) {
+__device__ __forceinline__ void afb_border_item(const AfbParams& p, const AfbLevel& lv, int plane, int it, bool active,
+                                                const unsigned* wait_ctr, unsigned wait_need) {
+    if (!active) it = 0;                             // idle threads shadow item 0 (they only take part in the wait)
     const int ncB = lv.Wo - 2 * lv.ncpA;             // border columns per output row
     const int i = it / ncB;
     const int e0 = it - i * ncB;
@@ -286,6 +289,11 @@ __device__ __forceinline__ void afb_border_item(const AfbParams& p, const AfbLev
         }
         cidx[j] = c;
     }
+    int srow[L];
+#pragma unroll
+    for (int jh = 0; jh < L; ++jh) srow[jh] = afb_src_row(2 * i + jh - lv.offH, lv.H, lv.Hreal, mode);
+    chain_wait(wait_ctr, wait_need);                 // index arithmetic above overlaps the wait
+    if (!active) return;
     const float* xp = lv.x + (long long)plane * lv.x_ps;
     // all L x L samples are loaded before any arithmetic (clamped address + select instead of branches), so
     // the thread pays one memory round trip; rows are done in chunks of <= 6 to bound the registers
@@ -298,7 +306,7 @@ __device__ __forceinline__ void afb_border_item(const AfbParams& p, const AfbLev
 #pragma unroll
         for (int jj = 0; jj < CH; ++jj) {
             const int jh = j0 + jj;
-            const int sr = jh < L ? afb_src_row(2 * i + jh - lv.offH, lv.H, lv.Hreal, mode) : -1;
+            const int sr = jh < L ? srow[jh < L ? jh : 0] : -1;
             rok[jj] = sr >= 0;
             const float* rowp = xp + (long long)max(sr, 0) * lv.x_rs;
 #pragma unroll
@@ -365,10 +373,8 @@ __global__ void __launch_bounds__(kStreamNT, AfbStreamCfg<L, S>::MINB) afb_strea
     if (cta < lv.cppA) {
         afb_ring_cta<L, S>(p, lv, plane, cta, ring_all, wait_ctr, wait_need, item);
     } else {
-        chain_wait(wait_ctr, wait_need);
-        TL_MARK(1);
         const int it = (cta - lv.cppA) * kStreamNT + tid;
-        if (it < lv.itemsB) afb_border_item<L, S>(p, lv, plane, it);
+        afb_border_item<L, S>(p, lv, plane, it, it < lv.itemsB, wait_ctr, wait_need);
     }
     TL_MARK(2);
     if (level + 1 < p.J) {
@@ -426,8 +432,9 @@ static int launch_afb_stream_t(AfbParams& p, int sms, cudaStream_t st) {
         // experiment knob: route small dependent levels through the one-thread-per-output path (measured slower:
         // profiles/r01_notes.md), off by default
         if (j > 0 && (long long)lv.Ho * lv.Wo <= env_int("B200W_DIRECT_MAX", 0)) lv.ncpA = 0;
-        // level 0 keeps the preferred length (measured best even when it leaves CTA slots empty); the dependent
-        // levels of a chain shrink until they fill the slots
+        // the first level keeps the preferred length (measured best even when it leaves CTA slots empty; an
+        // SM-balancing search over R was tried and was not better, profiles/r01_notes.md); the dependent levels of a
+        // chain shrink until they fill the resident slots
         int R = rpref;
         if (j > 0) {
             const int rmin = std::max(2, H2 - 1);

@@ -21,6 +21,7 @@
 // thread per output position.  A null `highs` means zeros (transform2d.py:137-139); out_h / out_w smaller than
 // the natural size crop.
 #include <algorithm>
+#include <cmath>
 #include "dwt_levels.cuh"
 
 namespace b200w {
@@ -266,8 +267,10 @@ __device__ __forceinline__ void sfb_ring_cta(const SfbParams& p, const SfbLevel&
 // All (L/2)^2 x 4 coefficients of an output are loaded before any arithmetic (clamped address + select), so the
 // thread pays one memory round trip; rows are done in chunks to bound the registers.
 template <int L>
-__device__ __forceinline__ void sfb_border_item(const SfbParams& p, const SfbLevel& lv, int plane, int it) {
+__device__ __forceinline__ void sfb_border_item(const SfbParams& p, const SfbLevel& lv, int plane, int it, bool active,
+                                                const unsigned* wait_ctr, unsigned wait_need) {
     constexpr int H2 = L / 2;
+    if (!active) it = 0;                             // idle threads shadow item 0 (they only take part in the wait)
     const int ncB = lv.nA0 + lv.out_w - lv.nA1;      // border columns per output row
     const int nH = it / ncB;
     const int e0 = it - nH * ncB;
@@ -285,6 +288,11 @@ __device__ __forceinline__ void sfb_border_item(const SfbParams& p, const SfbLev
         const int k = (AW >> 1) - u;
         kc[u] = (unsigned)k < (unsigned)w ? k : (periodic ? coef_index_far(k, w, periodic) : -1);
     }
+    int krow[H2];
+#pragma unroll
+    for (int u = 0; u < H2; ++u) krow[u] = sfb_src_row((AH >> 1) - u, h, periodic);
+    sfb_chain_wait(wait_ctr, wait_need);             // index arithmetic above overlaps the wait
+    if (!active) return;
     float y = 0.f;
     constexpr int CH = H2 < 3 ? H2 : 3;
 #pragma unroll
@@ -294,7 +302,7 @@ __device__ __forceinline__ void sfb_border_item(const SfbParams& p, const SfbLev
 #pragma unroll
         for (int uu = 0; uu < CH; ++uu) {
             const int uH = u0 + uu;
-            const int kr = uH < H2 ? sfb_src_row((AH >> 1) - uH, h, periodic) : -1;
+            const int kr = uH < H2 ? krow[uH < H2 ? uH : 0] : -1;
             rok[uu] = kr >= 0;
             const int row = max(kr, 0);
             const float* lp = lowp + (long long)row * lv.low_rs;
@@ -355,9 +363,8 @@ __global__ void __launch_bounds__(kStreamNT, SfbStreamCfg<L, S2V>::MINB) sfb_str
         if (lv.vec2) sfb_ring_cta<L, 2, S2V>(p, lv, plane, cta, sfb_ring_all, wait_ctr, wait_need);
         else sfb_ring_cta<L, 1, 0>(p, lv, plane, cta, sfb_ring_all, wait_ctr, wait_need);
     } else {
-        sfb_chain_wait(wait_ctr, wait_need);
         const int it = (cta - lv.cppA) * kStreamNT + tid;
-        if (it < lv.itemsB) sfb_border_item<L>(p, lv, plane, it);
+        sfb_border_item<L>(p, lv, plane, it, it < lv.itemsB, wait_ctr, wait_need);
     }
     if (level + 1 < p.J) {
         __syncthreads();
