@@ -43,7 +43,7 @@ def _source_hash():
     files += [os.path.join(INCLUDE, f) for f in sorted(os.listdir(INCLUDE))]
     for f in files:
         with open(f, "rb") as fh:
-            h.update(f.encode())
+            h.update(os.path.basename(f).encode())   # not the absolute path: the tree is copied to other machines
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
@@ -57,13 +57,27 @@ def is_fresh():
 
 
 def build(force=False, verbose=False):
-    """Compile every ``csrc/*.cu`` into ``_lib/libb200wave.so``; returns its path."""
+    """Compile every ``csrc/*.cu`` into ``_lib/libb200wave.so``; returns its path.  Safe against concurrent callers
+    (one process per GPU under torchrun): an exclusive file lock serialises them and the library is moved into place
+    atomically, so nobody ever loads a half-written file."""
     if not force and is_fresh():
         return LIB_PATH
     nvcc = find_nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libb200wave.so (set NVCC=/path/to/nvcc)")
     os.makedirs(LIB_DIR, exist_ok=True)
+    import fcntl
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_fresh():   # somebody else built it while we waited
+                return LIB_PATH
+            return _build_locked(nvcc, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(nvcc, verbose):
     objs = []
     procs = []
     for src in SOURCES:
@@ -80,11 +94,13 @@ def build(force=False, verbose=False):
             print(out, file=sys.stderr)
         if pr.returncode != 0:
             raise RuntimeError("nvcc failed on %s:\n%s" % (src, out))
+    tmp = LIB_PATH + ".tmp.%d" % os.getpid()
     link = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
-            "-Xcompiler", "-fPIC", "-o", LIB_PATH] + objs
+            "-Xcompiler", "-fPIC", "-o", tmp] + objs
     res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n%s" % res.stdout)
+    os.replace(tmp, LIB_PATH)
     with open(STAMP, "w") as fh:
         fh.write(_source_hash())
     return LIB_PATH
