@@ -246,6 +246,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION/INFO
+        os.environ["NCCL_DEBUG"] = os.environ.get("B200W_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
 
     n, c, h, w = cfg["shape"]
