@@ -6,6 +6,7 @@ Drop-in surface (same names and signatures as the reference):
 * ``DWTForward``, ``DWTInverse`` and the aliases ``DWT``, ``IDWT``, ``DWT2D``, ``IDWT2D``
   (``pytorch_wavelets/__init__.py:24-33``), ``dwt.lowlevel.AFB2D`` / ``SFB2D`` / ``afb2d`` / ``sfb2d``
 * ``SSIM``, ``ssim`` (``ssim.py``)
+* ``freq.high_pass``, ``freq.low_pass`` (``utils.py:93-117``) and the batched ``freq.gaussian_split``
 * ``HostPipeline``: host-buffer front end (chunked, stream-overlapped H2D | kernels | D2H)
 
 Everything computes in hand-written CUDA kernels behind ``torch.ops.b200wave``;
@@ -18,6 +19,7 @@ from .dwt.transform2d import DWTForward, DWTInverse
 from .ssim import SSIM, ssim
 from .wavelets import Wavelet, wavelist  # noqa: F401
 from .hostpipe import HostPipeline
+from . import freq  # noqa: F401  (utils.high_pass / low_pass)
 
 __version__ = "0.1.0"
 

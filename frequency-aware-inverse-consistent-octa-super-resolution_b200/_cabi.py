@@ -52,6 +52,9 @@ SYMBOLS = {
     "b200w_idwt2_f32": (_i, [_vp, _i64, _i64, _c_vp_p, _i, _c_int_p, _c_int_p,
                              _c_float_p, _c_float_p, _i, _c_float_p, _c_float_p, _i,
                              _i, _i, _c_int_p, _c_int_p, _vp, _vp, _sz, _vp]),
+    "b200w_freq_mask_c64": (_i, [_vp, _i, _i, _i, ctypes.c_float, _i, _vp]),
+    "b200w_abs_sign_f32": (_i, [_vp, _vp, _sz, ctypes.c_float, _vp]),
+    "b200w_sign_mul_f32": (_i, [_vp, _vp, _vp, _sz, ctypes.c_float, _vp]),
     "b200w_ssim_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "b200w_ssim_fwd_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _c_float_p, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "b200w_ssim_bwd_f32": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _c_float_p, _i, _i, _vp, _vp, _vp]),

@@ -46,3 +46,13 @@ def install(force=False):
     ssim_mod.__b200wave_alias__ = True
     sys.modules["ssim"] = ssim_mod
     return pw
+
+
+def patch_utils(utils_module):
+    """Point ``utils.high_pass`` / ``utils.low_pass`` of an already imported reference ``utils`` module
+    (``utils.py:93-117``; called at ``train.py:173-213``) at the batched CUDA implementation in ``b200wave.freq``.
+    Everything else in that module is left alone."""
+    from b200wave import freq
+    utils_module.high_pass = freq.high_pass
+    utils_module.low_pass = freq.low_pass
+    return utils_module

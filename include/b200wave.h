@@ -18,6 +18,8 @@
  *   b200w_idwt2_f32     pw/dwt/transform2d.py:134-148  the J-level loop of DWTInverse.forward over SFB2D.apply incl.
  *                       the 'unpad' crop, and the backward of DWTForward (J x AFB2D.backward) -- ONE launch
  *   b200w_dwt_coeff_len pywt.dwt_coeff_len as called at pw/dwt/lowlevel.py:153
+ *   b200w_freq_mask_c64 / b200w_abs_sign_f32 / b200w_sign_mul_f32
+ *                       utils.py:71-117  Gaussian low / high pass in the Fourier domain
  *
  * Conventions
  *   - every image pointer is DEVICE memory owned by the caller (torch); the library never
@@ -142,6 +144,19 @@ int b200w_idwt2_f32(const float* yl, int64_t yl_plane_stride, int64_t yl_row_str
                     const float* h_lo, const float* h_hi, int Lh,
                     int mode, int J, const int* out_h, const int* out_w, float* y,
                     void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Fourier-domain Gaussian frequency split, utils.py:71-117 (guais_low_pass / guais_high_pass / high_pass / low_pass):
+ * the pointwise passes around the FFTs (which the caller runs with cuFFT, e.g. torch.fft.rfft2 / irfft2).
+ * b200w_freq_mask_c64: in place on the half spectrum of rfft2, (planes, rows, cols/2+1) interleaved complex64;
+ *   multiplies bin (u,v) by exp(-0.5 (du^2+dv^2)/radius^2) (1 - that when highpass), du/dv the signed frequencies --
+ *   the mask of utils.py:71-91 without materialising or shifting it.
+ * b200w_abs_sign_f32: y = sign * |x|  (high_pass: +1, utils.py:103; low_pass: -1, utils.py:117).
+ * b200w_sign_mul_f32: out = g * sign * sgn(x), the backward of abs_sign.
+ */
+int b200w_freq_mask_c64(void* spec, int planes, int rows, int cols, float radius, int highpass, void* stream);
+int b200w_abs_sign_f32(const float* x, float* y, size_t n, float sign, void* stream);
+int b200w_sign_mul_f32(const float* g, const float* x, float* out, size_t n, float sign, void* stream);
 
 /*
  * SSIM forward.  img1,img2: (N,C,H,W) dense.  win: `ws` HOST floats, the normalised 1-D Gaussian

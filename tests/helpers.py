@@ -53,3 +53,17 @@ def case_filters(case):
     """(h_col, h_row, g_col, g_row) pairs of prepped taps as the reference's buffers hold them."""
     return ((case["h0_col"], case["h1_col"]), (case["h0_row"], case["h1_row"]),
             (case["g0_col"], case["g1_col"]), (case["g0_row"], case["g1_row"]))
+
+
+def load_freq_cases():
+    z = np.load(os.path.join(GOLDEN, "freq_cases.npz"))
+    cases = []
+    for i in range(int(z["ncases"])):
+        pre = "f%02d/" % i
+        case = {k[len(pre):]: z[k] for k in z.files if k.startswith(pre)}
+        case["radius"] = int(case["radius"])
+        case["highpass"] = bool(case["highpass"])
+        case["id"] = "%02d-%s-r%d-%dx%d" % (i, "high" if case["highpass"] else "low", case["radius"],
+                                            case["x"].shape[-2], case["x"].shape[-1])
+        cases.append(case)
+    return cases

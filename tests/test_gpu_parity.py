@@ -13,8 +13,8 @@ import torch
 
 import b200wave
 from b200wave import lowlevel
-from oracle import dwt_oracle, ssim_oracle
-from helpers import RTOL_F32, case_filters, load_dwt_cases, load_ssim_cases, rel_err
+from oracle import dwt_oracle, freq_oracle, ssim_oracle
+from helpers import RTOL_F32, case_filters, load_dwt_cases, load_freq_cases, load_ssim_cases, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -384,3 +384,35 @@ def test_alternative_kernel_paths(env):
                          cwd=root, env=child_env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
                          timeout=1500)
     assert res.returncode == 0, res.stdout[-3000:]
+
+
+FREQ_CASES = load_freq_cases()
+
+
+@pytest.mark.parametrize("case", FREQ_CASES, ids=[c["id"] for c in FREQ_CASES])
+def test_golden_freq_split(case):
+    """b200wave.freq.high_pass / low_pass (same signature as utils.py:93-117) vs the reference's own outputs."""
+    from b200wave import freq
+    t = cu(case["x"])
+    out = freq.high_pass(t, i=case["radius"]) if case["highpass"] else freq.low_pass(t, i=case["radius"])
+    assert tuple(out.shape) == case["y"].shape and out.is_contiguous()
+    assert rel_err(out.cpu(), case["y"]) < RTOL_F32
+
+
+def test_freq_split_batched_and_gradient():
+    """Batched form == per-image calls == float64 oracle; gradient == oracle (self-adjoint filter, sgn through abs)."""
+    from b200wave import freq
+    rng = np.random.default_rng(11)
+    x = rng.random((3, 2, 96, 80)).astype(np.float32)
+    g = rng.standard_normal((3, 2, 96, 80)).astype(np.float32)
+    for radius, hp, sign in [(10, True, 1.0), (8, False, -1.0)]:
+        tx = cu(x, grad=True)
+        out = freq.gaussian_split(tx, radius, hp, sign)
+        ref = freq_oracle.split(x, radius, hp, sign)
+        assert rel_err(out.detach().cpu(), ref) < RTOL_F32
+        one = (freq.high_pass if hp else freq.low_pass)(cu(x[1, 1][None]), i=radius)
+        assert rel_err(one.cpu(), ref[1, 1]) < RTOL_F32
+        out.backward(cu(g))
+        assert rel_err(tx.grad.cpu(), freq_oracle.split_backward(x, g, radius, hp, sign)) < RTOL_F32
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        freq.high_pass(torch.rand(1, 8, 8))

@@ -3,8 +3,8 @@
 import numpy as np
 import pytest
 
-from oracle import dwt_oracle, ssim_oracle
-from helpers import load_dwt_cases, load_ssim_cases, case_filters, rel_err
+from oracle import dwt_oracle, freq_oracle, ssim_oracle
+from helpers import load_dwt_cases, load_freq_cases, load_ssim_cases, case_filters, rel_err
 
 DWT_CASES = load_dwt_cases()
 SSIM_CASES = load_ssim_cases()
@@ -87,3 +87,32 @@ def test_known_answers():
     # ssim(x, x) == 1
     a = np.random.default_rng(1).random((1, 2, 20, 20))
     assert abs(ssim_oracle.ssim(a, a) - 1.0) < 1e-12
+
+
+FREQ_CASES = load_freq_cases()
+
+
+@pytest.mark.parametrize("case", FREQ_CASES, ids=[c["id"] for c in FREQ_CASES])
+def test_freq_split_oracle_vs_reference(case):
+    """utils.high_pass / utils.low_pass of the unmodified reference (fp32 FFT) vs the float64 restatement."""
+    fn = freq_oracle.high_pass if case["highpass"] else freq_oracle.low_pass
+    out = fn(case["x"], case["radius"])
+    assert out.shape == case["y"].shape
+    assert rel_err(out, case["y"]) < 3e-6        # the reference itself is fp32
+    assert (out >= 0).all() if case["highpass"] else (out <= 0).all()      # low_pass returns -|.| (utils.py:117)
+
+
+def test_freq_split_backward_is_the_gradient():
+    """oracle backward (self-adjoint filter, sgn through abs) == finite differences of the oracle forward."""
+    rng = np.random.default_rng(3)
+    x = rng.random((12, 10))
+    g = rng.standard_normal((12, 10))
+    for hp, sign in [(True, 1.0), (False, -1.0)]:
+        d = freq_oracle.split_backward(x, g, 3, hp, sign)
+        eps = 1e-6
+        for (i, j) in [(0, 0), (5, 7), (11, 9)]:
+            xp, xm = x.copy(), x.copy()
+            xp[i, j] += eps
+            xm[i, j] -= eps
+            fd = (g * (freq_oracle.split(xp, 3, hp, sign) - freq_oracle.split(xm, 3, hp, sign))).sum() / (2 * eps)
+            assert abs(fd - d[i, j]) < 1e-6 * max(1.0, abs(fd))

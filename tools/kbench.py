@@ -74,7 +74,38 @@ def ssim_case(n, h, w):
               24 * px / tb / 1e9, 20 * px / (t3 + tb) / 1e9, 20 * px / (t3 + tb) / 1e9 / PEAK * 100), flush=True)
 
 
+def freq_case(n, h, w, radius=10):
+    """Fourier-domain split (utils.py:93-117 batched): whole call and the pointwise kernels alone."""
+    import time
+    import numpy as np
+    from b200wave import freq
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import freq_oracle
+    nsets = max(2, int(2 * 126e6 * 1.05 / (4 * n * h * w)) + 1)
+    xs = [torch.rand(n, 1, h, w, device=dev) for _ in range(nsets)]
+    specs = [torch.fft.rfft2(x).contiguous() for x in xs]
+    with torch.no_grad():
+        t_all = timeit(lambda i: freq.gaussian_split(xs[i % nsets], radius, True, 1.0), nsets)
+        t_mask = timeit(lambda i: torch.ops.b200wave_freq.mask_(specs[i % nsets], h, w, float(radius), True), nsets)
+        t_abs = timeit(lambda i: torch.ops.b200wave_freq.abs_sign(xs[i % nsets], 1.0), nsets)
+    px = n * h * w
+    mask_bytes = 16 * n * h * (w // 2 + 1)
+    xc = xs[0][:4].cpu().numpy()
+    t0 = time.perf_counter()
+    freq_oracle.split(xc, radius, True, 1.0)
+    t_cpu = (time.perf_counter() - t0) / 4 * n
+    print("freq %4dx%4dx%4d r=%d  split %7.1f us %6.1f Gpx/s | mask kernel %6.1f us %5.0f GB/s (%4.1f%%) | abs kernel %6.1f us "
+          "%5.0f GB/s (%4.1f%%) | numpy fp64 (1 core) %8.1f ms" % (
+              n, h, w, radius, t_all * 1e6, px / t_all / 1e9, t_mask * 1e6, mask_bytes / t_mask / 1e9,
+              mask_bytes / t_mask / 1e9 / PEAK * 100, t_abs * 1e6, 8 * px / t_abs / 1e9, 8 * px / t_abs / 1e9 / PEAK * 100,
+              t_cpu * 1e3), flush=True)
+
+
 what = (sys.argv[1] if len(sys.argv) > 1 else "all") if __name__ == "__main__" else "none"
+if what in ("freq", "all"):
+    freq_case(64, 256, 256)
+    freq_case(256, 256, 256)
+    freq_case(64, 1024, 1024)
 if what in ("dwt", "all"):
     dwt_case(64, 304, 304, "db3", "symmetric")
     dwt_case(64, 154, 154, "db3", "symmetric")
