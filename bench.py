@@ -377,10 +377,12 @@ def main():
     e2e_steps = max(3, min(args.steps, 50))
     for i in range(3):
         e2e_step(i)
+    pipe.join()
     barrier()
     ev0.record()
     for i in range(e2e_steps):
-        e2e_step(i)
+        e2e_step(i)          # steps stream through the upload / compute / download queues back to back
+    pipe.join()              # the timed region ends when the last step's results are in host memory
     ev1.record()
     barrier()
     e2e_ms = ev0.elapsed_time(ev1)

@@ -91,13 +91,21 @@ class HostPipeline(object):
         d2h = sum(t.numel() * t.element_size() for t, _ in self.host_out)
         return h2d, d2h
 
+    def join(self):
+        """Make the current stream wait for every result copy issued so far (device-side; does not block the host)."""
+        torch.cuda.current_stream(self.device).wait_stream(self.s_out)
+
     def __call__(self, host_inputs, sync=True):
-        """Copy in, run, copy out, chunk by chunk; returns the tuple of pinned result tensors (valid after the
-        call when ``sync`` is true, else after ``self.s_out.synchronize()``)."""
+        """Copy in, run, copy out, chunk by chunk; returns the tuple of pinned result tensors.  They are valid after
+        the call when ``sync`` is true.  With ``sync=False`` nothing waits: consecutive calls stream through the
+        three queues back to back (call N+1's uploads overlap call N's downloads); use ``join()`` /
+        ``s_out.synchronize()`` before reading the results, and note that the same pinned result buffers are reused by
+        every call."""
         if self.host_out is None:
             self.host_out = self._alloc_host_out()
         cur = torch.cuda.current_stream(self.device)
-        self.s_in.wait_stream(cur)
+        if sync:
+            self.s_in.wait_stream(cur)   # inputs produced by work queued on the caller's stream
         for k, (lo, hi) in enumerate(self.bounds):
             with torch.cuda.stream(self.s_in):
                 self.s_in.wait_event(self.ev_free[k])     # previous call's kernels are done with these buffers
@@ -119,7 +127,7 @@ class HostPipeline(object):
                 for (h, per_sample), o in zip(self.host_out, self.dev_out[k]):
                     (h[lo:hi] if per_sample else h[k]).copy_(o, non_blocking=True)
                 self.ev_out[k].record(self.s_out)
-        cur.wait_stream(self.s_out)
         if sync:
+            cur.wait_stream(self.s_out)
             self.s_out.synchronize()
         return tuple(h for h, _ in self.host_out)
