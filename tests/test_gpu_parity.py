@@ -416,3 +416,26 @@ def test_freq_split_batched_and_gradient():
         assert rel_err(tx.grad.cpu(), freq_oracle.split_backward(x, g, radius, hp, sign)) < RTOL_F32
     with pytest.raises(RuntimeError, match="CUDA-only"):
         freq.high_pass(torch.rand(1, 8, 8))
+
+
+def test_more_levels_than_one_launch_holds():
+    """J > B200W_MAX_LEVELS (8): DWTForward / DWTInverse split the chain into several launches."""
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((1, 2, 600, 520)).astype(np.float32)
+    J = 9
+    xfm = b200wave.DWTForward(J=J, wave="db1", mode="zero").to(DEV)
+    ifm = b200wave.DWTInverse(wave="db1", mode="zero").to(DEV)
+    hc = (xfm.h0_col.flatten().cpu().numpy().astype(np.float64), xfm.h1_col.flatten().cpu().numpy().astype(np.float64))
+    gc = (ifm.g0_col.flatten().cpu().numpy().astype(np.float64), ifm.g1_col.flatten().cpu().numpy().astype(np.float64))
+    tx = cu(x, grad=True)
+    yl, yh = xfm(tx)
+    assert len(yh) == J
+    oyl, oyh = dwt_oracle.dwt_forward(x.astype(np.float64), J, hc, hc, "zero")
+    assert rel_err(yl.detach().cpu(), oyl) < RTOL_F32
+    for a, b in zip(yh, oyh):
+        assert rel_err(a.detach().cpu(), b) < RTOL_F32
+    rec = ifm((yl, yh))
+    orec = dwt_oracle.dwt_inverse(oyl, oyh, gc, gc, "zero")
+    assert rel_err(rec.detach().cpu(), orec) < RTOL_F32
+    rec.sum().backward()
+    assert tx.grad is not None and torch.isfinite(tx.grad).all()
