@@ -244,10 +244,14 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    saved_stdout = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION/INFO
-        os.environ["NCCL_DEBUG"] = os.environ.get("B200W_NCCL_DEBUG", "WARN")
+        # keep stdout to the one JSON line: NCCL printf()s its version banner there when the first communicator is
+        # created, so file descriptor 1 points at stderr until the line is printed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     n, c, h, w = cfg["shape"]
@@ -498,7 +502,10 @@ def main():
             "gpu_launches": my_kernels_per_step * args.steps,
             "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks,
         }
-        print(json.dumps(line))
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
