@@ -429,9 +429,6 @@ static int launch_afb_stream_t(AfbParams& p, int sms, cudaStream_t st) {
         if (cpR > lv.Wo / 2) cpR = lv.Wo / 2;
         lv.ncpA = cpR - lv.cp0A;
         if (lv.ncpA < kMinColPairs) lv.ncpA = 0;              // too narrow for the ring: all columns take the border path
-        // experiment knob: route small dependent levels through the one-thread-per-output path (measured slower:
-        // profiles/r01_notes.md), off by default
-        if (j > 0 && (long long)lv.Ho * lv.Wo <= env_int("B200W_DIRECT_MAX", 0)) lv.ncpA = 0;
         // the first level keeps the preferred length (measured best even when it leaves CTA slots empty; an
         // SM-balancing search over R was tried and was not better, profiles/r01_notes.md); the dependent levels of a
         // chain shrink until they fill the resident slots
@@ -442,7 +439,6 @@ static int launch_afb_stream_t(AfbParams& p, int sms, cudaStream_t st) {
                 R = std::max(rmin, R - 2);
         }
         if (stream_rows_override() > 0) R = stream_rows_override();
-        if (j > 0 && env_int("B200W_STREAM_ROWS_HI", 0) > 0) R = env_int("B200W_STREAM_ROWS_HI", 0);
         if (R > lv.Ho) R = lv.Ho;
         lv.R = R;
         const int nseg = ceil_div(lv.Ho, R);
@@ -456,10 +452,6 @@ static int launch_afb_stream_t(AfbParams& p, int sms, cudaStream_t st) {
     }
     p.total = base;
     if (base > 0x7fffffffLL) return B200W_ERR_BAD_SHAPE;
-    {   // timing experiment only (results incomplete): run just the first k levels of the chain
-        const int k = env_int("B200W_DEBUG_LEVELS", 0);
-        if (k > 0 && k < p.J) base = p.lv[k].cta_base;
-    }
     if (p.J > 1) {
         const int rc = zero_sync_words(p.ticket, (size_t)p.J * p.planes + 1, st);
         if (rc) return rc;

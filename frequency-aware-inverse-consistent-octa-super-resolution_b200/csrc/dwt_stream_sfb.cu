@@ -420,8 +420,6 @@ static int launch_sfb_stream_t(SfbParams& p, int sms, cudaStream_t st) {
         lv.tA0 = t0;
         lv.ntA = t1 - t0;
         if (lv.ntA < kSfbMinThreads) lv.ntA = 0;   // too narrow for the ring: every column takes the border path
-        // experiment knob (see the analysis launcher), off by default
-        if (j + 1 < p.J && (long long)lv.out_h * lv.out_w <= sfb_env_int("B200W_DIRECT_MAX", 0)) lv.ntA = 0;
         lv.nA0 = lv.ntA > 0 ? 4 * lv.tA0 + lv.n0_off : lv.out_w;
         lv.nA1 = lv.ntA > 0 ? 4 * (lv.tA0 + lv.ntA) + lv.n0_off : lv.out_w;
         const int npairs = ((lv.offH + lv.out_h - 1) >> 1) + 1 - lv.m_lo;
