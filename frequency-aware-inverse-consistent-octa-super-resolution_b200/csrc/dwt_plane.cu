@@ -94,8 +94,6 @@ __global__ void __launch_bounds__(kPlaneNT, 1) afb_plane_kernel(const __grid_con
 
     float* in = bufA;
     float* out = bufB;
-    const int lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = kPlaneNT / 32;
     for (int j = first; j < p.J; ++j) {
         const AfbLevel& lv = p.lv[j];
         const int Hreal = lv.Hreal, Wreal = lv.Wreal, H = lv.H, W = lv.W;
@@ -105,82 +103,117 @@ __global__ void __launch_bounds__(kPlaneNT, 1) afb_plane_kernel(const __grid_con
         const int OP = pitch4i(Wo);          // output (next input) pitch
         const int ncp = (Wo + 1) >> 1;
         float* mlo = mid;
-        float* mhi = mid + (size_t)Hreal * MP;
+        float* mhi = mid + Hreal * MP;
         // index maps of the padding mode, once per level: columns -(offW+S) .. and rows -offH ..
         const int ncm = 4 * ncp + NE, nrm = 2 * Ho + L;
         for (int k = tid; k < ncm; k += kPlaneNT) s_cmap[k] = afb_map(k - (offW + S), W, Wreal, mode);
         for (int k = tid; k < nrm; k += kPlaneNT) s_rmap[k] = afb_map(k - offH, H, Hreal, mode);
         __syncthreads();
-        // ---- row pass: a warp per input row, a lane per output column pair ----------------------------
-        for (int r = warp; r < Hreal; r += NW) {
-            const float* row = in + (size_t)r * P;
-            for (int cp = lane; cp < ncp; cp += 32) {
-                const int cb = 4 * cp - (offW + S);
-                float v[NE];
-                if (cb >= 0 && cb + NE <= Wreal) {
+        // ---- row pass.  Interior column pairs: a thread keeps ONE pair and walks down the rows (constant window
+        // offset, pointer increments only); the 2-8 border pairs of a row go through the column map afterwards.
+        const int cp0 = (offW + S) >> 2;
+        int cpR = Wreal + offW + S - NE >= 0 ? (Wreal + offW + S - NE) / 4 + 1 : 0;
+        if (cpR > ncp) cpR = ncp;
+        const int ncpI = cpR > cp0 ? cpR - cp0 : 0;
+        if (ncpI > 0) {
+            const int RG = kPlaneNT / ncpI > 0 ? kPlaneNT / ncpI : 1;
+            for (int t0 = tid; t0 < RG * ncpI; t0 += kPlaneNT) {   // one trip unless the row is wider than the CTA
+                const int rg = t0 / ncpI, cp = cp0 + (t0 - rg * ncpI);
+                const float* row = in + rg * P + (4 * cp - (offW + S));
+                float* dlo = mlo + rg * MP + 2 * cp;
+                float* dhi = mhi + rg * MP + 2 * cp;
+                for (int r = rg; r < Hreal; r += RG, row += RG * P, dlo += RG * MP, dhi += RG * MP) {
+                    float v[NE];
 #pragma unroll
                     for (int q = 0; q < NV; ++q) {
-                        const float4 t = reinterpret_cast<const float4*>(row + cb)[q];
+                        const float4 t = reinterpret_cast<const float4*>(row)[q];
                         v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
                     }
-                } else {
+                    float lo0 = 0.f, lo1 = 0.f, hi0 = 0.f, hi1 = 0.f;
 #pragma unroll
-                    for (int e = 0; e < NE; ++e) {
-                        const int c = s_cmap[4 * cp + e];
-                        v[e] = c >= 0 ? row[c] : 0.f;
+                    for (int t = 0; t < L; ++t) {
+                        lo0 = fmaf(p.t.w_lo[t], v[S + t], lo0);
+                        hi0 = fmaf(p.t.w_hi[t], v[S + t], hi0);
+                        lo1 = fmaf(p.t.w_lo[t], v[S + t + 2], lo1);
+                        hi1 = fmaf(p.t.w_hi[t], v[S + t + 2], hi1);
                     }
+                    *reinterpret_cast<float2*>(dlo) = make_float2(lo0, lo1);
+                    *reinterpret_cast<float2*>(dhi) = make_float2(hi0, hi1);
                 }
+            }
+        }
+        {
+            const int nE = ncp - ncpI;
+            for (int it = tid; it < nE * Hreal; it += kPlaneNT) {
+                const int r = it / nE, e = it - r * nE;
+                const int cp = e < cp0 || ncpI == 0 ? e : e - cp0 + cpR;
+                const float* row = in + r * P;
                 float lo0 = 0.f, lo1 = 0.f, hi0 = 0.f, hi1 = 0.f;
 #pragma unroll
-                for (int t = 0; t < L; ++t) {
-                    lo0 = fmaf(p.t.w_lo[t], v[S + t], lo0);
-                    hi0 = fmaf(p.t.w_hi[t], v[S + t], hi0);
-                    lo1 = fmaf(p.t.w_lo[t], v[S + t + 2], lo1);
-                    hi1 = fmaf(p.t.w_hi[t], v[S + t + 2], hi1);
+                for (int t = 0; t < L + 2; ++t) {
+                    const int c = s_cmap[4 * cp + S + t];
+                    const float x = c >= 0 ? row[c] : 0.f;
+                    if (t < L) { lo0 = fmaf(p.t.w_lo[t], x, lo0); hi0 = fmaf(p.t.w_hi[t], x, hi0); }
+                    if (t >= 2) { lo1 = fmaf(p.t.w_lo[t - 2], x, lo1); hi1 = fmaf(p.t.w_hi[t - 2], x, hi1); }
                 }
-                *reinterpret_cast<float2*>(mlo + (size_t)r * MP + 2 * cp) = make_float2(lo0, lo1);
-                *reinterpret_cast<float2*>(mhi + (size_t)r * MP + 2 * cp) = make_float2(hi0, hi1);
+                *reinterpret_cast<float2*>(mlo + r * MP + 2 * cp) = make_float2(lo0, lo1);
+                *reinterpret_cast<float2*>(mhi + r * MP + 2 * cp) = make_float2(hi0, hi1);
             }
         }
         __syncthreads();
-        // ---- column pass: a warp per output row ---------------------------------------------------------
-        const size_t band = (size_t)Ho * Wo;
+        // ---- column pass: a thread keeps one column pair and walks down the output rows -------------------
+        const int band = Ho * Wo;
         float* lowg = lv.low + (long long)plane * lv.low_ps;
-        float* hig = lv.highs + (size_t)plane * 3 * band;
+        float* hig = lv.highs + (size_t)plane * 3 * (size_t)band;
         const bool last = j + 1 == p.J;
-        const bool keep = !last;                   // LL feeds the next level from shared memory
         const bool v2hi = lv.out_vec2 != 0, v2lo = lv.low_vec2 != 0;
-        for (int i = warp; i < Ho; i += NW) {
-            int sr[L];
-#pragma unroll
-            for (int t = 0; t < L; ++t) sr[t] = s_rmap[2 * i + t];
-            for (int cp = lane; cp < ncp; cp += 32) {
+        const int low_rs = (int)lv.low_rs;
+        const int RGc = kPlaneNT / ncp > 0 ? kPlaneNT / ncp : 1;
+        for (int t0 = tid; t0 < RGc * ncp; t0 += kPlaneNT) {
+            const int ig = t0 / ncp, cp = t0 - ig * ncp;
+            const int k0 = 2 * cp;
+            const bool c1 = k0 + 1 < Wo;
+            for (int i = ig; i < Ho; i += RGc) {
                 float2 ll = make_float2(0.f, 0.f), lh = ll, hl = ll, hh = ll;
+                const int rf = 2 * i - offH;
+                if (rf >= 0 && rf + L <= Hreal) {   // all L source rows inside: straight strided reads
+                    const float* a0 = mlo + rf * MP + k0;
+                    const float* b0 = mhi + rf * MP + k0;
 #pragma unroll
-                for (int t = 0; t < L; ++t) {
-                    if (sr[t] >= 0) {   // warp-uniform
-                        const float2 a = *reinterpret_cast<const float2*>(mlo + (size_t)sr[t] * MP + 2 * cp);
-                        const float2 b = *reinterpret_cast<const float2*>(mhi + (size_t)sr[t] * MP + 2 * cp);
+                    for (int t = 0; t < L; ++t) {
+                        const float2 a = *reinterpret_cast<const float2*>(a0 + t * MP);
+                        const float2 b = *reinterpret_cast<const float2*>(b0 + t * MP);
                         const float gl = p.t.h_lo[t], gh = p.t.h_hi[t];
                         ll.x = fmaf(gl, a.x, ll.x); ll.y = fmaf(gl, a.y, ll.y);
                         lh.x = fmaf(gh, a.x, lh.x); lh.y = fmaf(gh, a.y, lh.y);
                         hl.x = fmaf(gl, b.x, hl.x); hl.y = fmaf(gl, b.y, hl.y);
                         hh.x = fmaf(gh, b.x, hh.x); hh.y = fmaf(gh, b.y, hh.y);
                     }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < L; ++t) {
+                        const int sr = s_rmap[2 * i + t];
+                        if (sr >= 0) {
+                            const float2 a = *reinterpret_cast<const float2*>(mlo + sr * MP + k0);
+                            const float2 b = *reinterpret_cast<const float2*>(mhi + sr * MP + k0);
+                            const float gl = p.t.h_lo[t], gh = p.t.h_hi[t];
+                            ll.x = fmaf(gl, a.x, ll.x); ll.y = fmaf(gl, a.y, ll.y);
+                            lh.x = fmaf(gh, a.x, lh.x); lh.y = fmaf(gh, a.y, lh.y);
+                            hl.x = fmaf(gl, b.x, hl.x); hl.y = fmaf(gl, b.y, hl.y);
+                            hh.x = fmaf(gh, b.x, hh.x); hh.y = fmaf(gh, b.y, hh.y);
+                        }
+                    }
                 }
-                const int k0 = 2 * cp;
-                const bool c1 = k0 + 1 < Wo;
-                if (keep) {
-                    float* o = out + (size_t)i * OP + k0;
+                if (!last) {   // LL feeds the next level from shared memory
+                    float* o = out + i * OP + k0;
                     o[0] = ll.x;
                     if (c1) o[1] = ll.y;
-                }
-                if (last) {   // the final low-pass image is an output
-                    float* q = lowg + (long long)i * lv.low_rs + k0;
+                } else {       // the final low-pass image is an output
+                    float* q = lowg + i * low_rs + k0;
                     if (v2lo && c1) *reinterpret_cast<float2*>(q) = ll;
                     else { q[0] = ll.x; if (c1) q[1] = ll.y; }
                 }
-                float* q = hig + (size_t)i * Wo + k0;
+                float* q = hig + i * Wo + k0;
                 if (v2hi && c1) {
                     *reinterpret_cast<float2*>(q) = lh;
                     *reinterpret_cast<float2*>(q + band) = hl;
