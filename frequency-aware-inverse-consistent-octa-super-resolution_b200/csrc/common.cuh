@@ -11,12 +11,34 @@ constexpr int kThreads = 256;
 
 // Filter taps travel by value in the kernel parameter block (constant bank): with the tap loops
 // fully unrolled every FFMA takes its coefficient as a c[0x0][..] operand, no load instruction.
+constexpr int kMaxTemplTaps = 16;   // tap counts the templated kernels are instantiated for
 struct Taps {
     float w_lo[kMaxTaps];  // along W
     float w_hi[kMaxTaps];
     float h_lo[kMaxTaps];  // along H
     float h_hi[kMaxTaps];
+    // the first kMaxTemplTaps H taps once more as (t, t) pairs: operands of the packed FFMA2 (fma.rn.f32x2), which
+    // takes them straight from uniform registers
+    float2 h_lo2[kMaxTemplTaps];
+    float2 h_hi2[kMaxTemplTaps];
 };
+
+// Blackwell packed fp32 FMA: (a.x*b.x + c.x, a.y*b.y + c.y) in one issue slot (SASS FFMA2)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(d)
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+          "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;"
+        : "=l"(d)
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
 
 // Extension index maps of mypad (pw/dwt/lowlevel.py:28-88) and of the periodization branch of
 // afb1d (:134-150), folded into one function: returns the source index in [0,n) or -1 for "zero".

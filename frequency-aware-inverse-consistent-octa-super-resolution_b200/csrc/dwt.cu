@@ -673,6 +673,10 @@ static int fill_taps(Taps& t, const float* w_lo, const float* w_hi, int Lw, cons
         t.h_lo[i] = i < Lh ? h_lo[i] : 0.f;
         t.h_hi[i] = i < Lh ? h_hi[i] : 0.f;
     }
+    for (int i = 0; i < kMaxTemplTaps; ++i) {
+        t.h_lo2[i] = make_float2(t.h_lo[i], t.h_lo[i]);
+        t.h_hi2[i] = make_float2(t.h_hi[i], t.h_hi[i]);
+    }
     return B200W_OK;
 }
 

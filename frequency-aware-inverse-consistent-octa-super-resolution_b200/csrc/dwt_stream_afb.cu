@@ -56,15 +56,17 @@ __device__ __forceinline__ int afb_src_row(int r, int H, int Hreal, int mode) {
     return sr >= Hreal ? -1 : sr;
 }
 
-// one pair of input rows: row pass for both, then scatter into the accumulator ring (ph = pair index mod L/2)
+// one pair of input rows: row pass for both, then scatter into the accumulator ring (ph = pair index mod L/2).
+// The ring keeps each sub-band's two columns as one float2, so the column pass runs on the packed FFMA2: the two
+// columns share the tap, which comes as a (t, t) pair from uniform registers.
 // With kRotate the ring is kept in age order instead (slot 0 = oldest) and shifted by the caller after the store:
 // L/2-1 register moves per row pair, but the loop needs no unrolling by L/2 -- for long filters the unrolled
 // body would not fit the instruction cache.
 template <int L, int S, int NE>
-__device__ __forceinline__ void afb_pair_fma(const Taps& t, const float (&v)[2][NE], float (&acc)[L / 2][8], int ph) {
+__device__ __forceinline__ void afb_pair_fma(const Taps& t, const float (&v)[2][NE], float2 (&acc)[L / 2][4], int ph) {
     constexpr int H2 = L / 2;
     constexpr bool kRotate = L >= 10;
-    float rl[2][2], rh[2][2];   // [row of the pair][column]
+    float2 rl[2], rh[2];   // [row of the pair] = (column 0, column 1)
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
         float lo0 = 0.f, lo1 = 0.f, hi0 = 0.f, hi1 = 0.f;
@@ -75,30 +77,31 @@ __device__ __forceinline__ void afb_pair_fma(const Taps& t, const float (&v)[2][
             lo1 = fmaf(t.w_lo[j], v[e][S + j + 2], lo1);
             hi1 = fmaf(t.w_hi[j], v[e][S + j + 2], hi1);
         }
-        rl[e][0] = lo0; rl[e][1] = lo1; rh[e][0] = hi0; rh[e][1] = hi1;
+        rl[e] = make_float2(lo0, lo1);
+        rh[e] = make_float2(hi0, hi1);
     }
     // this pair carries taps (2u, 2u+1) of output row q - u
 #pragma unroll
     for (int u = 0; u < H2; ++u) {
         const int sl = kRotate ? H2 - 1 - u : (ph - u + H2) % H2;
-        const float a = t.h_lo[2 * u], b = t.h_hi[2 * u];
-        const float c = t.h_lo[2 * u + 1], d = t.h_hi[2 * u + 1];
-        float* s = acc[sl];
+        const float2 a = t.h_lo2[2 * u], b = t.h_hi2[2 * u];
+        const float2 c = t.h_lo2[2 * u + 1], d = t.h_hi2[2 * u + 1];
+        float2* s = acc[sl];
         if (u == 0) {   // first contribution: start the accumulators
-            s[0] = a * rl[0][0]; s[1] = a * rl[0][1];
-            s[2] = b * rl[0][0]; s[3] = b * rl[0][1];
-            s[4] = a * rh[0][0]; s[5] = a * rh[0][1];
-            s[6] = b * rh[0][0]; s[7] = b * rh[0][1];
+            s[0] = fmul2(a, rl[0]);   // LL: W-lo, H-lo
+            s[1] = fmul2(b, rl[0]);   // LH: W-lo, H-hi
+            s[2] = fmul2(a, rh[0]);   // HL: W-hi, H-lo
+            s[3] = fmul2(b, rh[0]);   // HH
         } else {
-            s[0] = fmaf(a, rl[0][0], s[0]); s[1] = fmaf(a, rl[0][1], s[1]);
-            s[2] = fmaf(b, rl[0][0], s[2]); s[3] = fmaf(b, rl[0][1], s[3]);
-            s[4] = fmaf(a, rh[0][0], s[4]); s[5] = fmaf(a, rh[0][1], s[5]);
-            s[6] = fmaf(b, rh[0][0], s[6]); s[7] = fmaf(b, rh[0][1], s[7]);
+            s[0] = ffma2(a, rl[0], s[0]);
+            s[1] = ffma2(b, rl[0], s[1]);
+            s[2] = ffma2(a, rh[0], s[2]);
+            s[3] = ffma2(b, rh[0], s[3]);
         }
-        s[0] = fmaf(c, rl[1][0], s[0]); s[1] = fmaf(c, rl[1][1], s[1]);   // LL: W-lo, H-lo
-        s[2] = fmaf(d, rl[1][0], s[2]); s[3] = fmaf(d, rl[1][1], s[3]);   // LH: W-lo, H-hi
-        s[4] = fmaf(c, rh[1][0], s[4]); s[5] = fmaf(c, rh[1][1], s[5]);   // HL: W-hi, H-lo
-        s[6] = fmaf(d, rh[1][0], s[6]); s[7] = fmaf(d, rh[1][1], s[7]);   // HH
+        s[0] = ffma2(c, rl[1], s[0]);
+        s[1] = ffma2(d, rl[1], s[1]);
+        s[2] = ffma2(c, rh[1], s[2]);
+        s[3] = ffma2(d, rh[1], s[3]);
     }
 }
 
@@ -205,7 +208,7 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
         cp_async_commit();
     }
     TL_MARK(14);
-    float acc[H2][8];    // ring of pending output rows: LL.x LL.y LH.x LH.y HL.x HL.y HH.x HH.y
+    float2 acc[H2][4];   // ring of pending output rows: LL, LH, HL, HH, each (column 0, column 1)
     int st_r = 0, st_w = D - 1;
     constexpr bool kRotate = L >= 10;
     constexpr int UQ = kRotate ? 1 : H2;
@@ -233,19 +236,19 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
                     afb_pair_fma<L, S, NE>(p.t, v, acc, ph);
                     // output row q - (H2-1) has now seen all its L input rows
                     if (q >= H2 - 1 && q < npairs) {
-                        const float* s = acc[kRotate ? 0 : (ph + 1) % H2];
+                        const float2* s = acc[kRotate ? 0 : (ph + 1) % H2];
                         if (v2lo) {
-                            *reinterpret_cast<float2*>(q0) = make_float2(s[0], s[1]);
+                            *reinterpret_cast<float2*>(q0) = s[0];
                         } else {
-                            q0[0] = s[0]; q0[1] = s[1];
+                            q0[0] = s[0].x; q0[1] = s[0].y;
                         }
                         if (v2hi) {
-                            *reinterpret_cast<float2*>(q1) = make_float2(s[2], s[3]);
-                            *reinterpret_cast<float2*>(q1 + band) = make_float2(s[4], s[5]);
-                            *reinterpret_cast<float2*>(q1 + 2 * band) = make_float2(s[6], s[7]);
+                            *reinterpret_cast<float2*>(q1) = s[1];
+                            *reinterpret_cast<float2*>(q1 + band) = s[2];
+                            *reinterpret_cast<float2*>(q1 + 2 * band) = s[3];
                         } else {
-                            q1[0] = s[2]; q1[band] = s[4]; q1[2 * band] = s[6];
-                            q1[1] = s[3]; q1[band + 1] = s[5]; q1[2 * band + 1] = s[7];
+                            q1[0] = s[1].x; q1[band] = s[2].x; q1[2 * band] = s[3].x;
+                            q1[1] = s[1].y; q1[band + 1] = s[2].y; q1[2 * band + 1] = s[3].y;
                         }
                         q0 += low_rs;
                         q1 += Wo;
@@ -254,7 +257,7 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
 #pragma unroll
                         for (int k = 0; k + 1 < H2; ++k)
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) acc[k][i] = acc[k + 1][i];
+                            for (int i = 0; i < 4; ++i) acc[k][i] = acc[k + 1][i];
                     }
                 }
                 st_r = st_r + 1 == D ? 0 : st_r + 1;

@@ -160,7 +160,7 @@ __device__ __forceinline__ void sfb_ring_cta(const SfbParams& p, const SfbLevel&
         issue(s, s);
         cp_async_commit();
     }
-    float acc[H2][8];     // ring of pending output row pairs: even row x4 columns, odd row x4 columns
+    float2 acc[H2][4];    // ring of pending output row pairs: even row (cols 0-1, 2-3), odd row (cols 0-1, 2-3)
     int st_r = 0, st_w = D - 1;
     // long filters keep the accumulator ring in age order and shift it after each store instead of unrolling by
     // L/2 (the unrolled body would not fit the instruction cache)
@@ -203,47 +203,42 @@ __device__ __forceinline__ void sfb_ring_cta(const SfbParams& p, const SfbLevel&
                     lo[e] = a;
                     hi[e] = b;
                 }
-                // H synthesis: coefficient row q carries taps (2u, 2u+1) of output row pair q - (H2-1) + u
+                // H synthesis: coefficient row q carries taps (2u, 2u+1) of output row pair q - (H2-1) + u.  The
+                // accumulators hold two adjacent columns per float2, so the updates run on the packed FFMA2 with the
+                // (t, t) tap pairs from uniform registers.
+                const float2 lo01 = make_float2(lo[0], lo[1]), lo23 = make_float2(lo[2], lo[3]);
+                const float2 hi01 = make_float2(hi[0], hi[1]), hi23 = make_float2(hi[2], hi[3]);
 #pragma unroll
                 for (int u = H2 - 1; u >= 0; --u) {
                     const int sl = kRotate ? u : (ph + u + 1) % H2;
-                    const float a0 = p.t.h_lo[2 * u], b0 = p.t.h_hi[2 * u];
-                    const float a1 = p.t.h_lo[2 * u + 1], b1 = p.t.h_hi[2 * u + 1];
-                    float* s = acc[sl];
+                    const float2 a0 = p.t.h_lo2[2 * u], b0 = p.t.h_hi2[2 * u];
+                    const float2 a1 = p.t.h_lo2[2 * u + 1], b1 = p.t.h_hi2[2 * u + 1];
+                    float2* s = acc[sl];   // [0..1] even output row (columns 0-1, 2-3), [2..3] odd output row
                     if (u == H2 - 1) {   // first contribution to that pair
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            s[e] = lo[e] * a0;
-                            s[4 + e] = lo[e] * a1;
-                        }
+                        s[0] = fmul2(lo01, a0); s[1] = fmul2(lo23, a0);
+                        s[2] = fmul2(lo01, a1); s[3] = fmul2(lo23, a1);
                     } else {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            s[e] = fmaf(lo[e], a0, s[e]);
-                            s[4 + e] = fmaf(lo[e], a1, s[4 + e]);
-                        }
+                        s[0] = ffma2(lo01, a0, s[0]); s[1] = ffma2(lo23, a0, s[1]);
+                        s[2] = ffma2(lo01, a1, s[2]); s[3] = ffma2(lo23, a1, s[3]);
                     }
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        s[e] = fmaf(hi[e], b0, s[e]);
-                        s[4 + e] = fmaf(hi[e], b1, s[4 + e]);
-                    }
+                    s[0] = ffma2(hi01, b0, s[0]); s[1] = ffma2(hi23, b0, s[1]);
+                    s[2] = ffma2(hi01, b1, s[2]); s[3] = ffma2(hi23, b1, s[3]);
                 }
                 // pair q - (H2-1) is complete
                 if (q >= H2 - 1 && q < nrows) {
-                    const float* s = acc[kRotate ? 0 : (ph + 1) % H2];
+                    const float2* s = acc[kRotate ? 0 : (ph + 1) % H2];
 #pragma unroll
                     for (int r = 0; r < 2; ++r) {
                         const int row = nrow + r;
                         if (row >= 0 && row < out_h) {
                             float* d = yq + r * y_rs;
                             if (yv == 4) {
-                                *reinterpret_cast<float4*>(d) = make_float4(s[4 * r], s[4 * r + 1], s[4 * r + 2], s[4 * r + 3]);
+                                *reinterpret_cast<float4*>(d) = make_float4(s[2 * r].x, s[2 * r].y, s[2 * r + 1].x, s[2 * r + 1].y);
                             } else if (yv == 2) {
-                                *reinterpret_cast<float2*>(d) = make_float2(s[4 * r], s[4 * r + 1]);
-                                *reinterpret_cast<float2*>(d + 2) = make_float2(s[4 * r + 2], s[4 * r + 3]);
+                                *reinterpret_cast<float2*>(d) = s[2 * r];
+                                *reinterpret_cast<float2*>(d + 2) = s[2 * r + 1];
                             } else {
-                                d[0] = s[4 * r]; d[1] = s[4 * r + 1]; d[2] = s[4 * r + 2]; d[3] = s[4 * r + 3];
+                                d[0] = s[2 * r].x; d[1] = s[2 * r].y; d[2] = s[2 * r + 1].x; d[3] = s[2 * r + 1].y;
                             }
                         }
                     }
@@ -254,7 +249,7 @@ __device__ __forceinline__ void sfb_ring_cta(const SfbParams& p, const SfbLevel&
 #pragma unroll
                     for (int k = 0; k + 1 < H2; ++k)
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) acc[k][i] = acc[k + 1][i];
+                        for (int i = 0; i < 4; ++i) acc[k][i] = acc[k + 1][i];
                 }
                 st_r = st_r + 1 == D ? 0 : st_r + 1;
             }
