@@ -20,6 +20,7 @@ from .ssim import SSIM, ssim
 from .wavelets import Wavelet, wavelist  # noqa: F401
 from .hostpipe import HostPipeline
 from . import freq  # noqa: F401  (utils.high_pass / low_pass)
+from . import fsd  # noqa: F401  (FS_Discriminator*.filter_wavelet)
 
 __version__ = "0.1.0"
 

@@ -44,6 +44,9 @@ SYMBOLS = {
     "b200w_sfb2d_f32": (_i, [_vp, _i64, _i64, _vp, _i, _i, _i,
                              _c_float_p, _c_float_p, _i, _c_float_p, _c_float_p, _i,
                              _i, _vp, _i, _i, _vp]),
+    "b200w_afb2d_ex_f32": (_i, [_vp, _i64, _i64, _i, _i, _i,
+                                _c_float_p, _c_float_p, _i, _c_float_p, _c_float_p, _i,
+                                _i, _vp, _vp, ctypes.c_float, ctypes.c_float, _vp]),
     "b200w_dwt2_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i, _c_int_p]),
     "b200w_dwt2_f32": (_i, [_vp, _i64, _i64, _i, _i, _i,
                             _c_float_p, _c_float_p, _i, _c_float_p, _c_float_p, _i,

@@ -56,3 +56,23 @@ def patch_utils(utils_module):
     utils_module.high_pass = freq.high_pass
     utils_module.low_pass = freq.low_pass
     return utils_module
+
+
+def patch_model(model_module):
+    """Swap ``FS_DiscriminatorA.filter_wavelet`` / ``FS_DiscriminatorB.filter_wavelet`` of an already imported
+    reference ``model`` module (``model.py:166-179, 222-235``) for the fused analysis-kernel epilogue in
+    ``b200wave.fsd``.  The methods keep reading ``self.DWT2`` (its tap buffers and mode) and ``self.cs``, so the
+    discriminators' constructors, state dicts and ``forward`` are untouched."""
+    from b200wave import fsd
+    from b200wave.dwt import lowlevel
+
+    def make(variant):
+        def filter_wavelet(self, x, norm=True):
+            d = self.DWT2
+            taps = tuple(lowlevel.host_taps(f) for f in (d.h0_col, d.h1_col, d.h0_row, d.h1_row))
+            return fsd.filter_wavelet(x, self.cs, norm, variant, taps, d.mode)
+        return filter_wavelet
+
+    model_module.FS_DiscriminatorA.filter_wavelet = make("A")
+    model_module.FS_DiscriminatorB.filter_wavelet = make("B")
+    return model_module

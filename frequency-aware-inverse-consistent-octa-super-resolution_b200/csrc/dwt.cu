@@ -369,11 +369,13 @@ __global__ void __launch_bounds__(kThreads) afb2d_direct_kernel(const __grid_con
             hh = fmaf(p.t.h_hi[jh], hi, hh);
         }
         const size_t o = (size_t)i * lv.Wo + k;
-        lv.low[(long long)plane * lv.low_ps + (long long)i * lv.low_rs + k] = ll;
-        float* hip = lv.highs + (size_t)plane * 3 * band + o;
-        hip[0] = lh;
-        hip[band] = hl;
-        hip[2 * band] = hh;
+        if (lv.st_low) lv.low[(long long)plane * lv.low_ps + (long long)i * lv.low_rs + k] = ll;
+        if (lv.st_hi) {
+            float* hip = lv.highs + (size_t)plane * 3 * band + o;
+            hip[0] = fmaf(lh, lv.hi_scale, lv.hi_shift);
+            hip[band] = fmaf(hl, lv.hi_scale, lv.hi_shift);
+            hip[2 * band] = fmaf(hh, lv.hi_scale, lv.hi_shift);
+        }
     }
 }
 
@@ -869,10 +871,12 @@ static size_t afb_workspace_bytes(int planes, int H, int W, int Lw, int Lh, int 
 static int run_afb_chain(const float* x, int64_t x_ps, int64_t x_rs, int planes, int H, int W, const float* w_lo,
                          const float* w_hi, int Lw, const float* h_lo, const float* h_hi, int Lh, int mode, int J,
                          const int* pad_hw, float* yl, float* const* highs, void* workspace, size_t workspace_bytes,
-                         cudaStream_t st) {
+                         cudaStream_t st, float hi_scale = 1.f, float hi_shift = 0.f, bool allow_skip = false) {
     if (!mode_supported(mode)) return B200W_ERR_BAD_MODE;
     if (J < 1 || J > kMaxLevels) return B200W_ERR_BAD_SHAPE;
-    if (!x || !yl || !highs) return B200W_ERR_NULL_POINTER;
+    // the filter_wavelet entry point (single level) may leave out the low-pass or the detail output
+    if (!x || !highs || (!allow_skip && !yl) || (allow_skip && !yl && !highs[0])) return B200W_ERR_NULL_POINTER;
+    const bool plain = !allow_skip && hi_scale == 1.f && hi_shift == 0.f;
     if (planes < 1 || H < 1 || W < 1) return B200W_ERR_BAD_SHAPE;
     AfbParams p;
     int rc = fill_taps(p.t, w_lo, w_hi, Lw, h_lo, h_hi, Lh);
@@ -893,8 +897,12 @@ static int run_afb_chain(const float* x, int64_t x_ps, int64_t x_rs, int planes,
     int h = H, w = W;  // real size of the level input
     for (int j = 0; j < J; ++j) {
         AfbLevel& lv = p.lv[j];
-        if (!highs[j]) return B200W_ERR_NULL_POINTER;
+        if (!highs[j] && !allow_skip) return B200W_ERR_NULL_POINTER;
         const int ph = (pad_hw && j > 0) ? pad_hw[2 * j] : 0, pw = (pad_hw && j > 0) ? pad_hw[2 * j + 1] : 0;
+        lv.st_low = (j < J - 1 || yl != nullptr) ? 1 : 0;
+        lv.st_hi = highs[j] != nullptr ? 1 : 0;
+        lv.hi_scale = hi_scale;
+        lv.hi_shift = hi_shift;
         if (j == 0) {
             lv.x = x;
             lv.x_ps = x_ps;
@@ -928,17 +936,18 @@ static int run_afb_chain(const float* x, int64_t x_ps, int64_t x_rs, int planes,
         if ((lv.offW % 2) == 0 && (lv.x_rs % 2) == 0 && (lv.x_ps % 2) == 0 && aligned_to(lv.x, 8)) lv.in_vec = 2;
         if (lv.in_vec == 2 && (lv.offW % 4) == 0 && (lv.x_rs % 4) == 0 && (lv.x_ps % 4) == 0 && aligned_to(lv.x, 16))
             lv.in_vec = 4;
-        lv.out_vec2 = ((lv.Wo % 2) == 0 && aligned_to(lv.highs, 8)) ? 1 : 0;
-        lv.low_vec2 = ((lv.low_rs % 2) == 0 && (lv.low_ps % 2) == 0 && aligned_to(lv.low, 8)) ? 1 : 0;
+        lv.out_vec2 = ((lv.Wo % 2) == 0 && lv.highs && aligned_to(lv.highs, 8)) ? 1 : 0;
+        lv.low_vec2 = ((lv.low_rs % 2) == 0 && (lv.low_ps % 2) == 0 && lv.low && aligned_to(lv.low, 8)) ? 1 : 0;
         lv.tile_base = lv.cta_base = 0;
         lv.tiles_h = lv.tiles_w = lv.R = lv.ncp = lv.cpp = lv.cp0A = lv.ncpA = lv.itemsA = lv.cppA = lv.RB = lv.itemsB = 0;
         h = lv.Ho;
         w = lv.Wo;
     }
-    if (templated_taps(Lw, Lh)) {
+    // the store epilogue lives in the stream and the direct kernels: other inputs (unaligned rows) take the direct one
+    if (templated_taps(Lw, Lh) && (plain || (!force_tiled() && afb_stream_supported(p, Lw)))) {
         // levels whose input plane fits in shared memory run plane-resident (one launch for all of them); the
         // bigger levels before them go through the stream chain (or the tile chain when rows are unaligned)
-        int first = (force_tiled() || no_plane()) ? J : afb_plane_first(p, Lw);
+        int first = (force_tiled() || no_plane() || !plain) ? J : afb_plane_first(p, Lw);
         if (first < J) {
             if (first > 0) {
                 AfbParams head = p;
@@ -1127,6 +1136,16 @@ extern "C" int b200w_afb2d_f32(const float* x, int64_t x_plane_stride, int64_t x
     float* his[1] = {highs};
     return run_afb_chain(x, x_plane_stride, x_row_stride, planes, H, W, w_lo, w_hi, Lw, h_lo, h_hi, Lh, mode, 1,
                          nullptr, low, his, nullptr, 0, (cudaStream_t)stream);
+}
+
+extern "C" int b200w_afb2d_ex_f32(const float* x, int64_t x_plane_stride, int64_t x_row_stride, int planes, int H,
+                                  int W, const float* w_lo, const float* w_hi, int Lw, const float* h_lo,
+                                  const float* h_hi, int Lh, int mode, float* low, float* highs, float hi_scale,
+                                  float hi_shift, void* stream) {
+    if (!mode_supported(mode)) return B200W_ERR_BAD_MODE;
+    float* his[1] = {highs};
+    return run_afb_chain(x, x_plane_stride, x_row_stride, planes, H, W, w_lo, w_hi, Lw, h_lo, h_hi, Lh, mode, 1,
+                         nullptr, low, his, nullptr, 0, (cudaStream_t)stream, hi_scale, hi_shift, true);
 }
 
 extern "C" int b200w_dwt2_f32(const float* x, int64_t x_plane_stride, int64_t x_row_stride, int planes, int H, int W,

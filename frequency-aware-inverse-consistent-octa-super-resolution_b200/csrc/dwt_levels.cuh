@@ -40,6 +40,10 @@ struct AfbLevel {
     int offH, offW;
     int out_vec2;          // 64-bit stores into highs allowed
     int low_vec2;          // 64-bit stores into low allowed
+    // store epilogue (FS_Discriminator.filter_wavelet, model.py:166-179): a sub-band whose pointer is null is not
+    // written, and the three detail bands are stored as hi_scale * v + hi_shift (1, 0 = plain DWT)
+    int st_low, st_hi;
+    float hi_scale, hi_shift;
     // tile kernels
     long long tile_base;   // index of this level's first tile in the global tile order
     int tiles_h, tiles_w;

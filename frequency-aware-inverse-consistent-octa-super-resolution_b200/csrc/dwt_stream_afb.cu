@@ -191,9 +191,11 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
     const int Wo = lv.Wo;
     const size_t band = (size_t)lv.Ho * Wo;
     const bool v2lo = lv.low_vec2 != 0, v2hi = lv.out_vec2 != 0;
+    const bool st_low = lv.st_low != 0, st_hi = lv.st_hi != 0;
+    const float2 hsc = make_float2(lv.hi_scale, lv.hi_scale), hsh = make_float2(lv.hi_shift, lv.hi_shift);
     const long long low_rs = lv.low_rs;
-    float* q0 = lv.low + (long long)plane * lv.low_ps + (long long)i0 * low_rs + 2 * cp;
-    float* q1 = lv.highs + (size_t)plane * 3 * band + (size_t)i0 * Wo + 2 * cp;
+    float* q0 = lv.low + (long long)plane * lv.low_ps + (long long)i0 * low_rs + 2 * cp;   // only dereferenced if st_low
+    float* q1 = lv.highs + (size_t)plane * 3 * band + (size_t)i0 * Wo + 2 * cp;            // ... if st_hi
 
     // warp-uniform trip count (lanes of a warp may sit in segments of different length)
     int npw = npairs;
@@ -237,18 +239,23 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
                     // output row q - (H2-1) has now seen all its L input rows
                     if (q >= H2 - 1 && q < npairs) {
                         const float2* s = acc[kRotate ? 0 : (ph + 1) % H2];
-                        if (v2lo) {
-                            *reinterpret_cast<float2*>(q0) = s[0];
-                        } else {
-                            q0[0] = s[0].x; q0[1] = s[0].y;
+                        if (st_low) {
+                            if (v2lo) {
+                                *reinterpret_cast<float2*>(q0) = s[0];
+                            } else {
+                                q0[0] = s[0].x; q0[1] = s[0].y;
+                            }
                         }
-                        if (v2hi) {
-                            *reinterpret_cast<float2*>(q1) = s[1];
-                            *reinterpret_cast<float2*>(q1 + band) = s[2];
-                            *reinterpret_cast<float2*>(q1 + 2 * band) = s[3];
-                        } else {
-                            q1[0] = s[1].x; q1[band] = s[2].x; q1[2 * band] = s[3].x;
-                            q1[1] = s[1].y; q1[band + 1] = s[2].y; q1[2 * band + 1] = s[3].y;
+                        if (st_hi) {
+                            const float2 lh = ffma2(s[1], hsc, hsh), hl = ffma2(s[2], hsc, hsh), hh = ffma2(s[3], hsc, hsh);
+                            if (v2hi) {
+                                *reinterpret_cast<float2*>(q1) = lh;
+                                *reinterpret_cast<float2*>(q1 + band) = hl;
+                                *reinterpret_cast<float2*>(q1 + 2 * band) = hh;
+                            } else {
+                                q1[0] = lh.x; q1[band] = hl.x; q1[2 * band] = hh.x;
+                                q1[1] = lh.y; q1[band + 1] = hl.y; q1[2 * band + 1] = hh.y;
+                            }
                         }
                         q0 += low_rs;
                         q1 += Wo;
@@ -335,11 +342,13 @@ __device__ __forceinline__ void afb_border_item(const AfbParams& p, const AfbLev
     }
     const size_t band = (size_t)lv.Ho * lv.Wo;
     const size_t o = (size_t)i * lv.Wo + k;
-    lv.low[(long long)plane * lv.low_ps + (long long)i * lv.low_rs + k] = ll;
-    float* hip = lv.highs + (size_t)plane * 3 * band + o;
-    hip[0] = lh;
-    hip[band] = hl;
-    hip[2 * band] = hh;
+    if (lv.st_low) lv.low[(long long)plane * lv.low_ps + (long long)i * lv.low_rs + k] = ll;
+    if (lv.st_hi) {
+        float* hip = lv.highs + (size_t)plane * 3 * band + o;
+        hip[0] = fmaf(lh, lv.hi_scale, lv.hi_shift);
+        hip[band] = fmaf(hl, lv.hi_scale, lv.hi_shift);
+        hip[2 * band] = fmaf(hh, lv.hi_scale, lv.hi_shift);
+    }
 }
 
 template <int L, int S>

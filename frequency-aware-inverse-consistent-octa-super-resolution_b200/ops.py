@@ -24,6 +24,8 @@ from . import _cabi
 _LIB = torch.library.Library("b200wave", "DEF")
 
 _LIB.define("afb2d(Tensor x, float[] w_lo, float[] w_hi, float[] h_lo, float[] h_hi, int mode) -> (Tensor, Tensor)")
+_LIB.define("afb2d_select(Tensor x, float[] w_lo, float[] w_hi, float[] h_lo, float[] h_hi, int mode, bool want_low, "
+            "bool want_highs, float hi_scale, float hi_shift) -> (Tensor, Tensor)")
 _LIB.define("sfb2d(Tensor low, Tensor? highs, float[] w_lo, float[] w_hi, float[] h_lo, float[] h_hi, int mode, "
             "int out_h, int out_w) -> Tensor")
 _LIB.define("dwt2(Tensor x, float[] w_lo, float[] w_hi, float[] h_lo, float[] h_hi, int mode, int J, int[] pad_hw) "
@@ -115,6 +117,77 @@ def _afb2d_fake(x, w_lo, w_hi, h_lo, h_hi, mode):
     N, C, H, W = x.shape
     Ho, Wo = coeff_len(H, len(h_lo), mode), coeff_len(W, len(w_lo), mode)
     return x.new_empty((N, C, Ho, Wo)), x.new_empty((N, C, 3, Ho, Wo))
+
+
+# ------------------------------------------------------------------------------------------- afb2d_select
+def _afb2d_select_cuda(x, w_lo, w_hi, h_lo, h_hi, mode, want_low, want_highs, hi_scale, hi_shift):
+    """One analysis level that writes only the sub-bands asked for, the detail bands as hi_scale*v + hi_shift
+    (FS_Discriminator.filter_wavelet, model.py:166-179): an output that is not wanted comes back with 0 elements
+    and costs no HBM traffic."""
+    _check_mode(mode)
+    _require_cuda_f32(x, "afb2d_select")
+    if x.dim() != 4:
+        raise IndexError("b200wave::afb2d_select expects a 4-D (N, C, H, W) tensor, got %d-D" % x.dim())
+    if not (want_low or want_highs):
+        raise ValueError("afb2d_select: at least one of the low-pass / detail outputs must be requested")
+    lib = _cabi.load()
+    N, C, H, W = x.shape
+    Lw, Lh = len(w_lo), len(h_lo)
+    if len(w_hi) != Lw or len(h_hi) != Lh:
+        raise RuntimeError("low- and high-pass filters must have the same length along an axis")
+    Ho, Wo = coeff_len(H, Lh, mode), coeff_len(W, Lw, mode)
+    low = torch.empty((N, C, Ho, Wo) if want_low else (0,), device=x.device, dtype=torch.float32)
+    highs = torch.empty((N, C, 3, Ho, Wo) if want_highs else (0,), device=x.device, dtype=torch.float32)
+    if N * C * Ho * Wo == 0:
+        return low, highs
+    xk, ps, rs = _planes_view(x)
+    a_wl, _ = _cabi.taps_array(w_lo)
+    a_wh, _ = _cabi.taps_array(w_hi)
+    a_hl, _ = _cabi.taps_array(h_lo)
+    a_hh, _ = _cabi.taps_array(h_hi)
+    with torch.cuda.device(x.device):
+        rc = lib.b200w_afb2d_ex_f32(xk.data_ptr(), ps, rs, N * C, H, W, a_wl, a_wh, Lw, a_hl, a_hh, Lh, int(mode),
+                                    low.data_ptr() if want_low else None, highs.data_ptr() if want_highs else None,
+                                    float(hi_scale), float(hi_shift), _stream())
+    _cabi.check(rc, _mode_name(mode))
+    return low, highs
+
+
+def _afb2d_select_fake(x, w_lo, w_hi, h_lo, h_hi, mode, want_low, want_highs, hi_scale, hi_shift):
+    N, C, H, W = x.shape
+    Ho, Wo = coeff_len(H, len(h_lo), mode), coeff_len(W, len(w_lo), mode)
+    return (x.new_empty((N, C, Ho, Wo) if want_low else (0,)),
+            x.new_empty((N, C, 3, Ho, Wo) if want_highs else (0,)))
+
+
+def _afb2d_select_setup(ctx, inputs, output):
+    x, w_lo, w_hi, h_lo, h_hi, mode, want_low, want_highs, hi_scale, _ = inputs
+    ctx.taps = (w_lo, w_hi, h_lo, h_hi)
+    ctx.mode = mode
+    ctx.in_shape = tuple(x.shape)
+    ctx.want = (want_low, want_highs)
+    ctx.hi_scale = hi_scale
+    ctx.set_materialize_grads(False)
+
+
+def _afb2d_select_backward(ctx, dlow, dhighs):
+    none = (None,) * 10
+    if not ctx.needs_input_grad[0]:
+        return none
+    want_low, want_highs = ctx.want
+    dlow = dlow if want_low else None
+    dhighs = dhighs if want_highs else None
+    if dlow is None and dhighs is None:
+        return none
+    N, C, H, W = ctx.in_shape
+    w_lo, w_hi, h_lo, h_hi = ctx.taps
+    if dlow is None:
+        dlow = dhighs.new_zeros((N, C) + tuple(dhighs.shape[-2:]))
+    if dhighs is not None and ctx.hi_scale != 1.0:
+        dhighs = dhighs * ctx.hi_scale   # d(hi_scale * v + hi_shift) / dv
+    # same pseudo-adjoint as AFB2D.backward (lowlevel.py:356-364); a missing detail gradient is never materialised
+    dx = torch.ops.b200wave.sfb2d(dlow, dhighs, w_lo, w_hi, h_lo, h_hi, ctx.mode, H, W)
+    return (dx,) + none[1:]
 
 
 # ------------------------------------------------------------------------------------------- sfb2d
@@ -503,6 +576,7 @@ _LIB.impl("dwt2", _dwt2_cuda, "CUDA")
 _LIB.impl("idwt2", _idwt2_cuda, "CUDA")
 _LIB.impl("ssim_fwd", _ssim_fwd_cuda, "CUDA")
 _LIB.impl("ssim_bwd", _ssim_bwd_cuda, "CUDA")
+_LIB.impl("afb2d_select", _afb2d_select_cuda, "CUDA")
 
 
 def _cpu_refuse(name):
@@ -512,11 +586,14 @@ def _cpu_refuse(name):
     return impl
 
 
-for _name in ("afb2d", "sfb2d", "dwt2", "idwt2", "ssim_fwd", "ssim_bwd"):
+for _name in ("afb2d", "afb2d_select", "sfb2d", "dwt2", "idwt2", "ssim_fwd", "ssim_bwd"):
     _LIB.impl(_name, _cpu_refuse(_name), "CPU")
 
 torch.library.register_fake("b200wave::afb2d", _afb2d_fake, lib=_LIB)
 torch.library.register_fake("b200wave::sfb2d", _sfb2d_fake, lib=_LIB)
+torch.library.register_fake("b200wave::afb2d_select", _afb2d_select_fake, lib=_LIB)
+torch.library.register_autograd("b200wave::afb2d_select", _afb2d_select_backward, setup_context=_afb2d_select_setup,
+                                lib=_LIB)
 torch.library.register_fake("b200wave::dwt2", _dwt2_fake, lib=_LIB)
 torch.library.register_fake("b200wave::idwt2", _idwt2_fake, lib=_LIB)
 torch.library.register_fake("b200wave::ssim_fwd", _ssim_fwd_fake, lib=_LIB)
@@ -526,6 +603,7 @@ torch.library.register_autograd("b200wave::sfb2d", _sfb2d_backward, setup_contex
 torch.library.register_autograd("b200wave::ssim_fwd", _ssim_backward, setup_context=_ssim_setup, lib=_LIB)
 
 afb2d = torch.ops.b200wave.afb2d
+afb2d_select = torch.ops.b200wave.afb2d_select
 sfb2d = torch.ops.b200wave.sfb2d
 dwt2 = torch.ops.b200wave.dwt2
 idwt2 = torch.ops.b200wave.idwt2

@@ -17,6 +17,8 @@
  *                       and the backward of DWTInverse (J x SFB2D.backward through the 'unpad' crops) -- ONE launch
  *   b200w_idwt2_f32     pw/dwt/transform2d.py:134-148  the J-level loop of DWTInverse.forward over SFB2D.apply incl.
  *                       the 'unpad' crop, and the backward of DWTForward (J x AFB2D.backward) -- ONE launch
+ *   b200w_afb2d_ex_f32  model.py:166-179, 222-235  FS_Discriminator.filter_wavelet: AFB2D + band selection + *0.5+0.5
+ *                       fused into the analysis kernel's stores
  *   b200w_dwt_coeff_len pywt.dwt_coeff_len as called at pw/dwt/lowlevel.py:153
  *   b200w_freq_mask_c64 / b200w_abs_sign_f32 / b200w_sign_mul_f32
  *                       utils.py:71-117  Gaussian low / high pass in the Fourier domain
@@ -99,6 +101,18 @@ int b200w_afb2d_f32(const float* x, int64_t x_plane_stride, int64_t x_row_stride
                     const float* w_lo, const float* w_hi, int Lw,
                     const float* h_lo, const float* h_hi, int Lh,
                     int mode, float* low, float* highs, void* stream);
+
+/*
+ * One analysis level with the store epilogue of FS_Discriminator.filter_wavelet (model.py:166-179, 222-235):
+ * `low` or `highs` may be NULL (that output is not written: cs='sum' uses only LL, cs='cat' only the detail bands),
+ * and the detail bands are stored as hi_scale * v + hi_shift (norm=True: 0.5, 0.5).  With C == 1 the (planes,3,Ho,Wo)
+ * `highs` is exactly torch.cat((LH, HL, HH), 1).
+ */
+int b200w_afb2d_ex_f32(const float* x, int64_t x_plane_stride, int64_t x_row_stride,
+                       int planes, int H, int W,
+                       const float* w_lo, const float* w_hi, int Lw,
+                       const float* h_lo, const float* h_hi, int Lh,
+                       int mode, float* low, float* highs, float hi_scale, float hi_shift, void* stream);
 
 /*
  * One synthesis level: low (planes,h,w) [strided], highs (planes,3,h,w) dense or NULL (= zeros,

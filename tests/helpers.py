@@ -67,3 +67,21 @@ def load_freq_cases():
                                             case["x"].shape[-2], case["x"].shape[-1])
         cases.append(case)
     return cases
+
+
+def load_fsd_cases():
+    z = np.load(os.path.join(GOLDEN, "fsd_cases.npz"))
+    cases = []
+    for i in range(int(z["ncases"])):
+        pre = "w%02d/" % i
+        case = {k[len(pre):]: z[k] for k in z.files if k.startswith(pre)}
+        case["variant"] = str(case["variant"])
+        case["cs"] = str(case["cs"])
+        case["norm"] = bool(case["norm"])
+        n = int(case["nbands"])
+        case["y"] = [case["y%d" % b] for b in range(n)]
+        case["g"] = [case["g%d" % b] for b in range(n)]
+        case["id"] = "%02d-%s-%s-norm%d-%dx%d" % (i, case["variant"], case["cs"], case["norm"],
+                                                  case["x"].shape[-2], case["x"].shape[-1])
+        cases.append(case)
+    return cases

@@ -13,8 +13,9 @@ import torch
 
 import b200wave
 from b200wave import lowlevel
-from oracle import dwt_oracle, freq_oracle, ssim_oracle
-from helpers import RTOL_F32, case_filters, load_dwt_cases, load_freq_cases, load_ssim_cases, rel_err
+from oracle import dwt_oracle, freq_oracle, fsd_oracle, ssim_oracle
+from helpers import (RTOL_F32, case_filters, load_dwt_cases, load_freq_cases, load_fsd_cases, load_ssim_cases,
+                     rel_err)
 
 pytestmark = pytest.mark.gpu
 
@@ -439,3 +440,108 @@ def test_more_levels_than_one_launch_holds():
     assert rel_err(rec.detach().cpu(), orec) < RTOL_F32
     rec.sum().backward()
     assert tx.grad is not None and torch.isfinite(tx.grad).all()
+
+
+FSD_CASES = load_fsd_cases()
+
+
+@pytest.mark.parametrize("case", FSD_CASES, ids=[c["id"] for c in FSD_CASES])
+def test_golden_filter_wavelet(case):
+    """b200wave.fsd.WaveletFilter vs FS_DiscriminatorA/B.filter_wavelet (model.py:166-179, 222-235): the reference's
+    own outputs and input gradients."""
+    from b200wave import fsd
+    filt = fsd.WaveletFilter(cs=case["cs"], variant=case["variant"]).to(DEV)
+    x = cu(case["x"], grad=True)
+    res = filt(x, case["norm"])
+    assert res[-1] is x and len(res) - 1 == len(case["y"])
+    for got, want in zip(res[:-1], case["y"]):
+        assert tuple(got.shape) == want.shape
+        assert rel_err(got.detach().cpu(), want) < RTOL_F32
+    (dx,) = torch.autograd.grad(list(res[:-1]), x, [cu(g) for g in case["g"]])
+    assert rel_err(dx.cpu(), case["dx"]) < RTOL_F32
+
+
+@pytest.mark.parametrize("shape", [(8, 1, 256, 256), (3, 1, 304, 304), (2, 1, 1024, 1024), (2, 2, 130, 74),
+                                   (1, 1, 67, 93), (5, 1, 2, 2)])
+def test_filter_wavelet_matches_unfused_path(shape):
+    """The store epilogue (skipped bands, 0.5*v+0.5) is bit-identical to DWTForward followed by the reference's
+    slicing and scaling (0.5*v is exact, so the fused multiply-add rounds like the separate multiply and add) -- at
+    the training crop size (train.py: 256x256), the BASELINE sizes and ragged ones; and it matches the oracle."""
+    from b200wave import fsd
+    rng = np.random.default_rng(shape[-1])
+    xn = rng.standard_normal(shape).astype(np.float32)
+    x = cu(xn)
+    xfm = b200wave.DWTForward(J=1, wave="haar", mode="reflect").to(DEV)
+    ll, (hi,) = xfm(x)
+    for variant in "AB":
+        for cs in ("sum", "each", "cat"):
+            for norm in (True, False):
+                got = fsd.filter_wavelet(x, cs, norm, variant)[:-1]
+                h = hi * 0.5 + 0.5 if norm else hi
+                if cs == "sum":
+                    want = (ll,) if variant == "A" else (h[:, :, 2],)
+                elif cs == "each":
+                    want = (ll, h[:, :, 0], h[:, :, 1], h[:, :, 2])
+                else:
+                    want = (torch.cat((h[:, :, 0], h[:, :, 1], h[:, :, 2]), 1),)
+                assert len(got) == len(want)
+                for a, b in zip(got, want):
+                    assert torch.equal(a, b), (variant, cs, norm)
+                ora = fsd_oracle.filter_wavelet(xn, cs, norm, variant)
+                for a, b in zip(got, ora):
+                    assert rel_err(a.cpu(), b) < RTOL_F32
+
+
+def test_filter_wavelet_other_filters_and_errors():
+    """Longer filters and other modes go through the same epilogue (stream ring, border items, direct kernel)."""
+    from b200wave import fsd, ops
+    rng = np.random.default_rng(5)
+    for wave, mode, shape in [("db2", "symmetric", (2, 1, 96, 200)), ("db4", "zero", (1, 2, 301, 77)),
+                              ("db3", "periodization", (2, 1, 64, 1000)), ("db8", "periodic", (1, 1, 200, 136))]:
+        x = cu(rng.standard_normal(shape).astype(np.float32))
+        ll, (hi,) = b200wave.DWTForward(J=1, wave=wave, mode=mode).to(DEV)(x)
+        filt = fsd.WaveletFilter(cs="each", wave=wave, mode=mode).to(DEV)
+        got = filt(x)
+        assert torch.equal(got[0], ll)
+        for b in range(3):
+            assert torch.equal(got[1 + b], hi[:, :, b] * 0.5 + 0.5)
+        cat = fsd.WaveletFilter(cs="cat", variant="B", wave=wave, mode=mode).to(DEV)(x, False)[0]
+        assert torch.equal(cat, torch.cat((hi[:, :, 0], hi[:, :, 1], hi[:, :, 2]), 1))
+        # a strided (non 16-byte-aligned) view takes the direct kernel
+        xs = x[..., 1:]
+        lls, (his,) = b200wave.DWTForward(J=1, wave=wave, mode=mode).to(DEV)(xs)
+        gs = filt(xs)
+        assert torch.equal(gs[0], lls) and torch.equal(gs[3], his[:, :, 2] * 0.5 + 0.5)
+    with pytest.raises(NotImplementedError, match="not recognized"):
+        fsd.filter_wavelet(x, cs="avg")
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        fsd.filter_wavelet(torch.rand(1, 1, 8, 8))
+    with pytest.raises(ValueError):
+        t = ops.afb2d_select(x, [1.0, 1.0], [1.0, -1.0], [1.0, 1.0], [1.0, -1.0], 4, False, False, 1.0, 0.0)
+
+
+def test_patch_model_swaps_the_discriminator_methods():
+    """compat.patch_model on a stand-in for the reference's model module: classes that, like FS_DiscriminatorA/B
+    (model.py:140-142, 190-192), own ``DWT2 = DWTForward(J=1, 'haar', 'reflect')`` and ``cs``."""
+    import types
+    from b200wave import compat
+
+    class A(torch.nn.Module):
+        def __init__(self, cs):
+            super().__init__()
+            self.DWT2 = b200wave.DWTForward(J=1, wave="haar", mode="reflect")
+            self.cs = cs
+
+        def filter_wavelet(self, x, norm=True):
+            raise AssertionError("not patched")
+
+    class B(A):
+        pass
+
+    mod = compat.patch_model(types.SimpleNamespace(FS_DiscriminatorA=A, FS_DiscriminatorB=B))
+    case = [c for c in FSD_CASES if c["variant"] == "B" and c["cs"] == "cat"][0]
+    got, x = mod.FS_DiscriminatorB("cat").to(DEV).filter_wavelet(cu(case["x"]), case["norm"])
+    assert rel_err(got.cpu(), case["y"][0]) < RTOL_F32
+    case = [c for c in FSD_CASES if c["variant"] == "A" and c["cs"] == "sum"][0]
+    got, x = mod.FS_DiscriminatorA("sum").to(DEV).filter_wavelet(cu(case["x"]), case["norm"])
+    assert rel_err(got.cpu(), case["y"][0]) < RTOL_F32

@@ -3,8 +3,8 @@
 import numpy as np
 import pytest
 
-from oracle import dwt_oracle, freq_oracle, ssim_oracle
-from helpers import load_dwt_cases, load_freq_cases, load_ssim_cases, case_filters, rel_err
+from oracle import dwt_oracle, freq_oracle, fsd_oracle, ssim_oracle
+from helpers import load_dwt_cases, load_freq_cases, load_fsd_cases, load_ssim_cases, case_filters, rel_err
 
 DWT_CASES = load_dwt_cases()
 SSIM_CASES = load_ssim_cases()
@@ -116,3 +116,29 @@ def test_freq_split_backward_is_the_gradient():
             xm[i, j] -= eps
             fd = (g * (freq_oracle.split(xp, 3, hp, sign) - freq_oracle.split(xm, 3, hp, sign))).sum() / (2 * eps)
             assert abs(fd - d[i, j]) < 1e-6 * max(1.0, abs(fd))
+
+
+FSD_CASES = load_fsd_cases()
+
+
+@pytest.mark.parametrize("case", FSD_CASES, ids=[c["id"] for c in FSD_CASES])
+def test_filter_wavelet_oracle_vs_reference(case):
+    """fsd_oracle vs outputs and input gradients of FS_DiscriminatorA/B.filter_wavelet (model.py:166-179, 222-235)."""
+    got = fsd_oracle.filter_wavelet(case["x"], case["cs"], case["norm"], case["variant"])
+    assert len(got) == len(case["y"])
+    for a, b in zip(got, case["y"]):
+        assert a.shape == b.shape and rel_err(a, b) < 1e-12
+    dx = fsd_oracle.filter_wavelet_backward(case["g"], case["x"].shape, case["cs"], case["norm"], case["variant"])
+    assert rel_err(dx, case["dx"]) < 1e-12
+
+
+def test_filter_wavelet_host_logic_without_gpu():
+    """Format validation happens on the host; a CPU tensor is refused (no CPU fallback)."""
+    import torch
+    from b200wave import fsd
+    with pytest.raises(NotImplementedError, match="not recognized"):
+        fsd.WaveletFilter(cs="avg")
+    filt = fsd.WaveletFilter(cs="cat", variant="B")
+    assert sorted(k for k in filt.state_dict()) == ["h0_col", "h0_row", "h1_col", "h1_row"]   # DWTForward's names
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        filt(torch.rand(1, 1, 8, 8))

@@ -101,7 +101,37 @@ def freq_case(n, h, w, radius=10):
               t_cpu * 1e3), flush=True)
 
 
+def fsd_case(n, h, w):
+    """filter_wavelet (model.py:166-179, 222-235): fused store epilogue vs DWTForward + slicing/scaling/cat."""
+    import b200wave
+    from b200wave import fsd
+    nsets = max(2, int(2 * 126e6 * 1.05 / (8 * n * h * w)) + 1)
+    xs = [torch.randn(n, 1, h, w, device=dev) for _ in range(nsets)]
+    xfm = b200wave.DWTForward(J=1, wave="haar", mode="reflect").to(dev)
+
+    def unfused(x, cs):
+        ll, (hi,) = xfm(x)
+        if cs == "sum":
+            return ll
+        lh, hl, hh = hi[:, :, 0] * 0.5 + 0.5, hi[:, :, 1] * 0.5 + 0.5, hi[:, :, 2] * 0.5 + 0.5
+        return torch.cat((lh, hl, hh), 1)
+
+    px = n * h * w
+    with torch.no_grad():
+        for cs, variant, bytes_px in (("sum", "A", 4 + 1), ("cat", "B", 4 + 3)):
+            t_f = timeit(lambda i: fsd.filter_wavelet(xs[i % nsets], cs, True, variant), nsets)
+            t_u = timeit(lambda i: unfused(xs[i % nsets], cs), nsets)
+            gbs = bytes_px * px / t_f / 1e9
+            print("fsd %4dx%4dx%4d cs=%-3s fused %7.1f us %6.0f GB/s (%4.1f%% of peak, %d B/px) | unfused %7.1f us | x%.2f" % (
+                n, h, w, cs, t_f * 1e6, gbs, gbs / PEAK * 100, bytes_px, t_u * 1e6, t_u / t_f), flush=True)
+
+
 what = (sys.argv[1] if len(sys.argv) > 1 else "all") if __name__ == "__main__" else "none"
+if what in ("fsd", "all"):
+    fsd_case(8, 256, 256)
+    fsd_case(64, 256, 256)
+    fsd_case(64, 304, 304)
+    fsd_case(64, 1024, 1024)
 if what in ("freq", "all"):
     freq_case(64, 256, 256)
     freq_case(256, 256, 256)
