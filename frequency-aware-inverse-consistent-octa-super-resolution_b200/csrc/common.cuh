@@ -42,7 +42,7 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
 
 // Extension index maps of mypad (pw/dwt/lowlevel.py:28-88) and of the periodization branch of
 // afb1d (:134-150), folded into one function: returns the source index in [0,n) or -1 for "zero".
-__device__ __forceinline__ int ext_index(int s, int n, int mode) {
+__host__ __device__ __forceinline__ int ext_index(int s, int n, int mode) {
     if ((unsigned)s < (unsigned)n) return s;
     switch (mode) {
         case B200W_MODE_SYMMETRIC: {  // half-sample symmetric, period 2n (utils.reflect(-0.5, n-0.5))

@@ -659,6 +659,26 @@ static bool no_plane() {
     if (v < 0) v = env_flag("B200W_PLANE");
     return v != 1;
 }
+// B200W_OWNER=0 switches the owner kernels off (chains of small planes then take the ticketed chain kernels);
+// B200W_OWNER_J0=n makes them start no earlier than level n (the levels before run as a chain launch).
+// B200W_OWNER=2 uses them whenever the shapes fit, however few planes there are (tests).
+static int owner_mode() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200W_OWNER");
+        v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+    }
+    return v;
+}
+static int owner_j0_min() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200W_OWNER_J0");
+        v = (e && *e) ? atoi(e) : 0;
+        if (v < 0) v = 0;
+    }
+    return v;
+}
 
 static bool mode_supported(int mode) {
     return mode == B200W_MODE_ZERO || mode == B200W_MODE_SYMMETRIC || mode == B200W_MODE_PERIODIZATION ||
@@ -947,6 +967,18 @@ static int run_afb_chain(const float* x, int64_t x_ps, int64_t x_rs, int planes,
     if (templated_taps(Lw, Lh) && (plain || (!force_tiled() && afb_stream_supported(p, Lw)))) {
         // levels whose input plane fits in shared memory run plane-resident (one launch for all of them); the
         // bigger levels before them go through the stream chain (or the tile chain when rows are unaligned)
+        if (J > 1 && !force_tiled() && owner_mode() != 0) {
+            AfbOwnerParams op;
+            if (afb_owner_plan(p, Lw, device_info().sms, owner_j0_min(), owner_mode() == 2, op)) {
+                if (op.j0 > 0) {
+                    AfbParams head = p;
+                    head.J = op.j0;
+                    rc = run_afb_big_levels(head, Lw, st);
+                    if (rc) return rc;
+                }
+                return launch_afb_owner(op, Lw, st);
+            }
+        }
         int first = (force_tiled() || no_plane() || !plain) ? J : afb_plane_first(p, Lw);
         if (first < J) {
             if (first > 0) {

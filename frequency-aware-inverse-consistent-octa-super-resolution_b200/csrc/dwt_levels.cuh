@@ -66,6 +66,27 @@ struct AfbParams {
     Taps t;
 };
 
+// "Owner" kernels (small planes, J > 1): one CTA owns a horizontal part of one plane for ALL levels from j0 on.  The
+// first of them streams its input rows from global memory, the low-pass image of every level but the last stays in
+// the CTA's shared memory, so the dependent levels cost a block barrier instead of a trip through L2 and a
+// grid-wide dependency.  Parts of a plane overlap by the few rows the deeper levels need (recomputed, not shared).
+constexpr int kMaxParts = 4;
+struct OwnerLevel {
+    int R;                 // output rows per thread segment
+    int pitch;             // row pitch (floats, multiple of 4) of this level's low-pass image in shared memory
+    int buf_off;           // its offset (floats) inside the low-pass area
+    int map_off;           // offset (ints) of this level's extension maps inside the map area
+    int c0[kMaxParts], c1[kMaxParts];   // output rows a part computes
+    int h0[kMaxParts], h1[kMaxParts];   // output rows a part stores to global memory (a partition of [0, Ho))
+};
+struct AfbOwnerParams {
+    AfbParams p;
+    OwnerLevel ol[kMaxLevels];
+    int j0, parts;
+    int ring_floats;       // size of the staging rings that precede the maps and the low-pass area
+    int map_ints;          // size of the extension-map area (all levels)
+};
+
 // ---- synthesis -----------------------------------------------------------------------------------
 struct SfbLevel {
     const float* low;
@@ -110,6 +131,12 @@ bool afb_stream_supported(const AfbParams& p, int L);
 int launch_afb_stream(AfbParams& p, int L, int sms, cudaStream_t st);
 bool sfb_stream_supported(const SfbParams& p, int L);
 int launch_sfb_stream(SfbParams& p, int L, int sms, cudaStream_t st);
+
+// owner kernel (dwt_stream_afb.cu): levels j0 .. J-1 of an analysis chain in one launch without grid-wide
+// dependencies.  afb_owner_plan fills `op` and returns true when the shapes qualify (low-pass images fit in shared
+// memory, enough planes x parts to occupy the device -- unless `force`); j0_min = first level it may start from.
+bool afb_owner_plan(const AfbParams& p, int L, int sms, int j0_min, bool force, AfbOwnerParams& op);
+int launch_afb_owner(const AfbOwnerParams& op, int L, cudaStream_t st);
 
 // plane-resident kernels (dwt_plane.cu): one CTA per plane runs the small levels of a transform in shared memory.
 // afb_plane_first = first analysis level from which on the rest fits (p.J = none); sfb_plane_count = number of

@@ -128,23 +128,46 @@ __device__ __forceinline__ void chain_wait(const unsigned* ctr, unsigned need) {
     }
 }
 
+// rows of a level that an owner CTA works on (owner kernel only): it computes output rows [c0, c1) -- all of them
+// feed its low-pass image in shared memory -- and stores the detail bands of rows [h0, h1) to global memory
+struct OwnRows {
+    int c0, c1, h0, h1;
+    int itemsA;            // thread items of the interior class over [c0, c1)
+    unsigned src_s;        // SMEM_SRC: shared address of the source image (row src_row0, column 0)
+    int src_row0;
+    // extension maps of the level in shared memory (the out-of-line index functions cost ~100 instructions per
+    // call, and an owner CTA runs its border items itself instead of spreading them over the device):
+    const int* rmap;       // rmap[r - (2*c0 - offH)] = source row of input row r, -1 = zero row
+    const int* cmap;       // cmap[c + offW] = source column of input column c, -1 = zero
+};
+
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
 // ---- interior column pairs: per-warp cp.async ring ---------------------------------------------------
-template <int L, int S>
-__device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel& lv, int plane, int cta, float4* ring_all,
-                                             const unsigned* wait_ctr, unsigned wait_need, unsigned item) {
+// `it` = the thread's item (segment-major: segment * ncpA + interior column pair).  OWNER: the rows come from `own`
+// instead of the whole level; SMEM_SRC (owner kernel, dependent levels): the input image already lies in shared
+// memory, so a lane reads its window straight from there and the ring is not used.
+template <int L, int S, bool OWNER = false, bool SMEM_SRC = false>
+__device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel& lv, int plane, int it, float4* ring_all,
+                                             const unsigned* wait_ctr, unsigned wait_need, unsigned item,
+                                             const OwnRows& own) {
     using C = AfbStreamCfg<L, S>;
     constexpr int H2 = C::H2, NV = C::NV, NE = C::NE, D = C::D;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int it = cta * kStreamNT + tid;
-    const bool active = it < lv.itemsA;
+    const int itemsA = OWNER ? own.itemsA : lv.itemsA;
+    const bool active = it < itemsA;
     const int ncpA = lv.ncpA;
-    const int itc = active ? it : lv.itemsA - 1;     // inactive lanes shadow the last item (no copies, no stores)
+    const int itc = active ? it : itemsA - 1;        // inactive lanes shadow the last item (no copies, no stores)
     const int seg = itc / ncpA;
     const int cpl = itc - seg * ncpA;
     const int cp = lv.cp0A + cpl;
-    const int i0 = seg * lv.R;                       // first output row of the segment
-    const int nout = min(lv.R, lv.Ho - i0);
+    const int i0 = (OWNER ? own.c0 : 0) + seg * lv.R;   // first output row of the segment
+    const int nout = min(lv.R, (OWNER ? own.c1 : lv.Ho) - i0);
     const int npairs = active ? nout + H2 - 1 : 0;   // input row pairs feeding them
     const int r0 = 2 * i0 - lv.offH;                 // first input row
     const int H = lv.H, Hreal = lv.Hreal, mode = p.mode;
@@ -164,10 +187,10 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
     auto issue = [&](int q, int st) {
         // nothing is staged beyond this lane's segment: the lanes that would read those slots (same run, same
         // segment) are past their last pair too, and an idle lane must not touch slots that belong to others
-        if (q < npairs) {
+        if (!SMEM_SRC && q < npairs) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int sr = afb_src_row(r0 + 2 * q + e, H, Hreal, mode);
+                const int sr = OWNER ? own.rmap[2 * (i0 - own.c0) + 2 * q + e] : afb_src_row(r0 + 2 * q + e, H, Hreal, mode);
                 const unsigned dst = ring_s + (unsigned)((st * 2 + e) * C::RP) * 16u;
                 if (sr >= 0) {
                     const float* src = xcol + (long long)sr * rs;
@@ -202,14 +225,19 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) npw = max(npw, __shfl_xor_sync(0xffffffffu, npw, o));
 
-    chain_wait(wait_ctr, wait_need);
+    if (!OWNER) chain_wait(wait_ctr, wait_need);
     TL_MARK(1);
+    if (!SMEM_SRC) {
 #pragma unroll 1
-    for (int s = 0; s < D - 1; ++s) {
-        issue(s, s);
-        cp_async_commit();
+        for (int s = 0; s < D - 1; ++s) {
+            issue(s, s);
+            cp_async_commit();
+        }
     }
     TL_MARK(14);
+    // SMEM_SRC: shared address of this lane's window in source row 0
+    const unsigned win_s = SMEM_SRC ? own.src_s + (unsigned)(cb - own.src_row0 * (int)rs) * 4u : 0u;
+    int orow = i0;         // OWNER: output row the next store belongs to
     float2 acc[H2][4];   // ring of pending output rows: LL, LH, HL, HH, each (column 0, column 1)
     int st_r = 0, st_w = D - 1;
     constexpr bool kRotate = L >= 10;
@@ -219,22 +247,38 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
         for (int ph = 0; ph < UQ; ++ph) {
             const int q = qb + ph;
             if (q < npw) {   // warp-uniform
-                cp_async_wait<D - 2>();   // this lane's copies of pair q have landed ...
-                __syncwarp();             // ... and everybody's; all lanes are done reading pair q-1
-                if (q < 4) TL_MARK(6 + 2 * q);
-                issue(q + D - 1, st_w);   // refill the stage pair q-1 was read from
-                cp_async_commit();
-                st_w = st_w + 1 == D ? 0 : st_w + 1;
+                if (!SMEM_SRC) {
+                    cp_async_wait<D - 2>();   // this lane's copies of pair q have landed ...
+                    __syncwarp();             // ... and everybody's; all lanes are done reading pair q-1
+                    if (q < 4) TL_MARK(6 + 2 * q);
+                    issue(q + D - 1, st_w);   // refill the stage pair q-1 was read from
+                    cp_async_commit();
+                    st_w = st_w + 1 == D ? 0 : st_w + 1;
+                }
                 {
                     float v[2][NE];
-                    const float4* src = ring + (st_r * 2) * C::RP + slot;
+                    if (SMEM_SRC) {
 #pragma unroll
-                    for (int e = 0; e < 2; ++e)
+                        for (int e = 0; e < 2; ++e) {
+                            const int sr = q < npairs ? own.rmap[2 * (i0 - own.c0) + 2 * q + e] : -1;
+                            const unsigned a = win_s + (unsigned)(max(sr, 0) * (int)rs) * 4u;
 #pragma unroll
-                        for (int k = 0; k < NV; ++k) {
-                            const float4 t = src[e * C::RP + k];
-                            v[e][4 * k] = t.x; v[e][4 * k + 1] = t.y; v[e][4 * k + 2] = t.z; v[e][4 * k + 3] = t.w;
+                            for (int k = 0; k < NV; ++k) {
+                                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (sr >= 0) t = lds128(a + 16u * k);
+                                v[e][4 * k] = t.x; v[e][4 * k + 1] = t.y; v[e][4 * k + 2] = t.z; v[e][4 * k + 3] = t.w;
+                            }
                         }
+                    } else {
+                        const float4* src = ring + (st_r * 2) * C::RP + slot;
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+#pragma unroll
+                            for (int k = 0; k < NV; ++k) {
+                                const float4 t = src[e * C::RP + k];
+                                v[e][4 * k] = t.x; v[e][4 * k + 1] = t.y; v[e][4 * k + 2] = t.z; v[e][4 * k + 3] = t.w;
+                            }
+                    }
                     afb_pair_fma<L, S, NE>(p.t, v, acc, ph);
                     // output row q - (H2-1) has now seen all its L input rows
                     if (q >= H2 - 1 && q < npairs) {
@@ -246,7 +290,7 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
                                 q0[0] = s[0].x; q0[1] = s[0].y;
                             }
                         }
-                        if (st_hi) {
+                        if (st_hi && (!OWNER || (orow >= own.h0 && orow < own.h1))) {
                             const float2 lh = ffma2(s[1], hsc, hsh), hl = ffma2(s[2], hsc, hsh), hh = ffma2(s[3], hsc, hsh);
                             if (v2hi) {
                                 *reinterpret_cast<float2*>(q1) = lh;
@@ -259,6 +303,7 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
                         }
                         q0 += low_rs;
                         q1 += Wo;
+                        if (OWNER) ++orow;
                     }
                     if (kRotate) {
 #pragma unroll
@@ -272,7 +317,7 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
             }
         }
     }
-    cp_async_wait<0>();
+    if (!SMEM_SRC) cp_async_wait<0>();
 }
 
 // ---- border columns: one thread per output position -----------------------------------------------------
@@ -280,20 +325,23 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
 // border column); its L x L input samples are independent loads through the row / column maps (one memory
 // latency instead of a dependent march), at the price of recomputing the row pass L/2 times -- for < 3 % of
 // the outputs.
-template <int L, int S>
+template <int L, int S, bool OWNER = false>
 __device__ __forceinline__ void afb_border_item(const AfbParams& p, const AfbLevel& lv, int plane, int it, bool active,
-                                                const unsigned* wait_ctr, unsigned wait_need) {
+                                                const unsigned* wait_ctr, unsigned wait_need, const OwnRows& own) {
     if (!active) it = 0;                             // idle threads shadow item 0 (they only take part in the wait)
     const int ncB = lv.Wo - 2 * lv.ncpA;             // border columns per output row
-    const int i = it / ncB;
-    const int e0 = it - i * ncB;
+    const int ib = it / ncB;
+    const int i = (OWNER ? own.c0 : 0) + ib;
+    const int e0 = it - ib * ncB;
     const int k = e0 < 2 * lv.cp0A ? e0 : e0 + 2 * lv.ncpA;   // left border columns, then right border columns
     const int mode = p.mode;
     int cidx[L];
 #pragma unroll
     for (int j = 0; j < L; ++j) {
         int c = 2 * k + j - lv.offW;
-        if ((unsigned)c >= (unsigned)lv.Wreal) {
+        if (OWNER) {
+            c = own.cmap[2 * k + j];
+        } else if ((unsigned)c >= (unsigned)lv.Wreal) {
             c = ext_index_far(c, lv.W, mode);
             if (c >= lv.Wreal) c = -1;
         }
@@ -301,8 +349,9 @@ __device__ __forceinline__ void afb_border_item(const AfbParams& p, const AfbLev
     }
     int srow[L];
 #pragma unroll
-    for (int jh = 0; jh < L; ++jh) srow[jh] = afb_src_row(2 * i + jh - lv.offH, lv.H, lv.Hreal, mode);
-    chain_wait(wait_ctr, wait_need);                 // index arithmetic above overlaps the wait
+    for (int jh = 0; jh < L; ++jh)
+        srow[jh] = OWNER ? own.rmap[2 * ib + jh] : afb_src_row(2 * i + jh - lv.offH, lv.H, lv.Hreal, mode);
+    if (!OWNER) chain_wait(wait_ctr, wait_need);     // index arithmetic above overlaps the wait
     if (!active) return;
     const float* xp = lv.x + (long long)plane * lv.x_ps;
     // all L x L samples are loaded before any arithmetic (clamped address + select instead of branches), so
@@ -343,7 +392,7 @@ __device__ __forceinline__ void afb_border_item(const AfbParams& p, const AfbLev
     const size_t band = (size_t)lv.Ho * lv.Wo;
     const size_t o = (size_t)i * lv.Wo + k;
     if (lv.st_low) lv.low[(long long)plane * lv.low_ps + (long long)i * lv.low_rs + k] = ll;
-    if (lv.st_hi) {
+    if (lv.st_hi && (!OWNER || (i >= own.h0 && i < own.h1))) {
         float* hip = lv.highs + (size_t)plane * 3 * band + o;
         hip[0] = fmaf(lh, lv.hi_scale, lv.hi_shift);
         hip[band] = fmaf(hl, lv.hi_scale, lv.hi_shift);
@@ -382,11 +431,12 @@ __global__ void __launch_bounds__(kStreamNT, AfbStreamCfg<L, S>::MINB) afb_strea
     // the previous level of this plane must be complete before its low-pass image is read
     const unsigned* wait_ctr = level > 0 ? p.done + (size_t)(level - 1) * p.planes + plane : nullptr;
     const unsigned wait_need = level > 0 ? (unsigned)p.lv[level - 1].cpp : 0u;
+    const OwnRows none{};
     if (cta < lv.cppA) {
-        afb_ring_cta<L, S>(p, lv, plane, cta, ring_all, wait_ctr, wait_need, item);
+        afb_ring_cta<L, S>(p, lv, plane, cta * kStreamNT + tid, ring_all, wait_ctr, wait_need, item, none);
     } else {
         const int it = (cta - lv.cppA) * kStreamNT + tid;
-        afb_border_item<L, S>(p, lv, plane, it, it < lv.itemsB, wait_ctr, wait_need);
+        afb_border_item<L, S>(p, lv, plane, it, it < lv.itemsB, wait_ctr, wait_need, none);
     }
     TL_MARK(2);
     if (level + 1 < p.J) {
@@ -394,6 +444,119 @@ __global__ void __launch_bounds__(kStreamNT, AfbStreamCfg<L, S>::MINB) afb_strea
         if (tid == 0) signal_done(p.done + (size_t)level * p.planes + plane);
     }
     TL_MARK(5);
+}
+
+// ---- owner kernel: levels j0 .. J-1 of one (plane, part) in one CTA -------------------------------------------
+// The first level streams from global memory through the same per-warp rings as above; its low-pass rows land in
+// shared memory, where the next level reads its windows directly (SMEM_SRC), and so on.  No tickets, no counters:
+// the only synchronisation is one block barrier per level.
+template <int L>
+struct AfbOwnerCfg {
+    // one CTA per SM; long filters need more than 128 registers per thread
+    static constexpr int NT = L <= 8 ? 512 : 256;
+};
+
+template <int L, int S>
+__global__ void __launch_bounds__(AfbOwnerCfg<L>::NT, 1) afb_owner_kernel(const __grid_constant__ AfbOwnerParams op) {
+    extern __shared__ float4 ring_all[];
+    constexpr int NT = AfbOwnerCfg<L>::NT;
+    const AfbParams& p = op.p;
+    const int tid = threadIdx.x;
+    const int plane = blockIdx.x / op.parts;
+    const int part = blockIdx.x - plane * op.parts;
+#ifdef B200W_TIMELINE
+    // slot 0 / 14: %globaltimer at start / end; slot 15: clock at start; slots 1 + 3*(j-j0) + {0,1,2}: clock after the
+    // maps, the interior passes and the border passes of level j
+#define OWN_MARK(slot, v) do { if (g_timeline && tid == 0) g_timeline[(size_t)blockIdx.x * 16 + (slot)] = (v); } while (0)
+    OWN_MARK(0, gtime());
+    OWN_MARK(15, (unsigned long long)clock64());
+#else
+#define OWN_MARK(slot, v) do { } while (0)
+#endif
+    int* const maps = reinterpret_cast<int*>(reinterpret_cast<float*>(ring_all) + op.ring_floats);
+    float* const ll_area = reinterpret_cast<float*>(maps) + op.map_ints;
+    // extension maps of every level, built once: input rows 2*c0 - offH + [0, 2*nrows + L) and input columns
+    // -offW + [0, 2*Wo + L) of level j at maps + map_off[j]
+#pragma unroll 1
+    for (int j = op.j0; j < p.J; ++j) {
+        const AfbLevel& lv = p.lv[j];
+        const OwnerLevel& ol = op.ol[j];
+        const int c0 = ol.c0[part];
+        const int nr = 2 * (ol.c1[part] - c0) + L, nc = 2 * lv.Wo + L;
+        int* const m_out = maps + ol.map_off;
+        for (int e = tid; e < nr + nc; e += NT) {
+            const bool row = e < nr;
+            const int s = row ? 2 * c0 - lv.offH + e : e - nr - lv.offW;
+            const int real = row ? lv.Hreal : lv.Wreal;
+            int m = s;
+            if ((unsigned)s >= (unsigned)real) {
+                m = ext_index_far(s, row ? lv.H : lv.W, p.mode);
+                if (m >= real) m = -1;
+            }
+            m_out[e] = m;
+        }
+    }
+    __syncthreads();
+    OWN_MARK(13, (unsigned long long)clock64());
+#pragma unroll 1
+    for (int j = op.j0; j < p.J; ++j) {
+        AfbLevel lv = p.lv[j];
+        const OwnerLevel& ol = op.ol[j];
+        OwnRows own;
+        own.c0 = ol.c0[part]; own.c1 = ol.c1[part]; own.h0 = ol.h0[part]; own.h1 = ol.h1[part];
+        own.src_s = 0; own.src_row0 = 0;
+        const bool smem_src = j > op.j0;
+        if (smem_src) {   // input = the previous level's low-pass rows [c0', c1') in shared memory
+            const OwnerLevel& pv = op.ol[j - 1];
+            float* buf = ll_area + pv.buf_off;
+            own.src_s = (unsigned)__cvta_generic_to_shared(buf);
+            own.src_row0 = pv.c0[part];
+            lv.x = buf - (long long)pv.c0[part] * pv.pitch;   // generic pointer for the border items
+            lv.x_ps = 0;
+            lv.x_rs = pv.pitch;
+        }
+        if (j + 1 < p.J) {   // low-pass output stays on chip
+            lv.low = ll_area + ol.buf_off - (long long)own.c0 * ol.pitch;
+            lv.low_ps = 0;
+            lv.low_rs = ol.pitch;
+            lv.low_vec2 = 1;
+            lv.st_low = 1;
+        }
+        lv.R = ol.R;
+        const int nrows = own.c1 - own.c0;
+        own.itemsA = ((nrows + lv.R - 1) / lv.R) * lv.ncpA;
+        own.rmap = maps + ol.map_off;
+        own.cmap = own.rmap + 2 * nrows + L;
+        OWN_MARK(1 + 3 * (j - op.j0), (unsigned long long)clock64());
+        const int itemsB = nrows * (lv.Wo - 2 * lv.ncpA);
+        const int padA = (own.itemsA + 31) & ~31;
+        // When the interior segments leave warps free (the plan sizes them so), those warps evaluate the border
+        // positions meanwhile; otherwise every thread does its interior items first and border items after, the
+        // border positions going to the last threads first (warps with no or short segments start them early).
+        const bool beside = itemsB > 0 && (NT - padA) * 4 >= itemsB;
+        const int ntA = beside ? padA : NT;
+        if (tid < ntA) {
+            for (int base = 0; base < own.itemsA; base += ntA) {
+                __syncwarp();   // the warp's ring is reused from pass to pass
+                if (smem_src)
+                    afb_ring_cta<L, S, true, true>(p, lv, plane, base + tid, ring_all, nullptr, 0u, 0u, own);
+                else
+                    afb_ring_cta<L, S, true, false>(p, lv, plane, base + tid, ring_all, nullptr, 0u, 0u, own);
+            }
+        }
+#ifdef B200W_TIMELINE
+        if (!beside) __syncthreads();
+        OWN_MARK(2 + 3 * (j - op.j0), (unsigned long long)clock64());
+#endif
+        if (!beside || tid >= padA) {
+            const int nb = beside ? NT - padA : NT;
+            for (int it = beside ? tid - padA : NT - 1 - tid; it < itemsB; it += nb)
+                afb_border_item<L, S, true>(p, lv, plane, it, true, nullptr, 0u, own);
+        }
+        __syncthreads();   // this level's low-pass rows are complete before the next level reads them
+        OWN_MARK(3 + 3 * (j - op.j0), (unsigned long long)clock64());
+    }
+    OWN_MARK(14, gtime());
 }
 
 static int env_int(const char* name, int dflt) {
@@ -495,6 +658,181 @@ template <int L>
 static int launch_afb_stream_l(AfbParams& p, int sms, cudaStream_t st) {
     if (p.mode == B200W_MODE_PERIODIZATION) return launch_afb_stream_t<L, afb_shift(L, true)>(p, sms, st);
     return launch_afb_stream_t<L, afb_shift(L, false)>(p, sms, st);
+}
+
+// interior / border split of the output columns of a level (the same for the stream and the owner kernel)
+template <int L, int S>
+static void afb_stream_columns(AfbLevel& lv) {
+    using C = AfbStreamCfg<L, S>;
+    lv.ncp = ceil_div(lv.Wo, 2);
+    lv.cp0A = (lv.offW + S) / 4;
+    int cpR = (lv.Wreal + lv.offW + S - C::NE) / 4 + 1;
+    if (lv.Wreal + lv.offW + S - C::NE < 0) cpR = 0;
+    if (cpR > lv.Wo / 2) cpR = lv.Wo / 2;
+    lv.ncpA = cpR - lv.cp0A;
+    if (lv.ncpA < kMinColPairs) lv.ncpA = 0;
+}
+
+constexpr size_t kOwnerSmemMax = 227 * 1024;
+// dynamic shared memory of the owner kernel: [rings | extension maps | low-pass images]
+
+template <int L, int S>
+static bool afb_owner_plan_t(const AfbParams& p, int sms, int j0_min, bool force, AfbOwnerParams& op) {
+    using C = AfbStreamCfg<L, S>;
+    constexpr int NT = AfbOwnerCfg<L>::NT;
+    constexpr int H2 = L / 2;
+    const int J = p.J;
+    if (J < 2 || j0_min > J - 2) return false;
+    const bool wraps = p.mode == B200W_MODE_PERIODIZATION || p.mode == B200W_MODE_PERIODIC;
+    int parts = std::min(kMaxParts, std::max(1, sms / p.planes));
+    if (wraps) parts = 1;   // a part would need rows from the far end of the image
+    parts = std::min(parts, p.lv[J - 1].Ho);
+    if (!force && (long long)p.planes * parts < sms / 2) return false;   // too few CTAs: the chain kernels spread better
+    op.p = p;
+    op.parts = parts;
+    op.ring_floats = (int)((size_t)(NT / 32) * C::D * C::STAGE * 4);
+    // rows: every level's output rows are split evenly over the parts (what a part stores); a part computes those
+    // plus whatever the next level's computed rows read through the row extension
+    for (int j = 0; j < J; ++j) {
+        afb_stream_columns<L, S>(op.p.lv[j]);
+        for (int q = 0; q < parts; ++q) {
+            op.ol[j].h0[q] = (int)((long long)p.lv[j].Ho * q / parts);
+            op.ol[j].h1[q] = (int)((long long)p.lv[j].Ho * (q + 1) / parts);
+        }
+    }
+    for (int q = 0; q < parts; ++q) {
+        op.ol[J - 1].c0[q] = op.ol[J - 1].h0[q];
+        op.ol[J - 1].c1[q] = op.ol[J - 1].h1[q];
+        for (int j = J - 2; j >= 0; --j) {
+            const AfbLevel& nx = p.lv[j + 1];   // reads this level's low-pass image
+            int lo = op.ol[j].h0[q], hi = op.ol[j].h1[q];
+            const int r_lo = 2 * op.ol[j + 1].c0[q] - nx.offH, r_hi = 2 * (op.ol[j + 1].c1[q] - 1) - nx.offH + L - 1;
+            for (int r = r_lo; r <= r_hi; ++r) {
+                int sr = r;
+                if (r < 0 || r >= nx.Hreal) {
+                    sr = ext_index(r, nx.H, p.mode);
+                    if (sr < 0 || sr >= nx.Hreal) continue;   // zero row
+                }
+                lo = std::min(lo, sr);
+                hi = std::max(hi, sr + 1);
+            }
+            op.ol[j].c0[q] = lo;
+            op.ol[j].c1[q] = hi;
+        }
+    }
+    // start at the first level from which on the low-pass images fit next to the rings
+    for (int j0 = j0_min; j0 <= J - 2; ++j0) {
+        size_t floats = 0;
+        for (int j = j0; j < J - 1; ++j) {
+            int rows = 0;
+            for (int q = 0; q < parts; ++q) rows = std::max(rows, op.ol[j].c1[q] - op.ol[j].c0[q]);
+            op.ol[j].pitch = (p.lv[j].Wo + 3) / 4 * 4;
+            op.ol[j].buf_off = (int)floats;
+            floats += (size_t)rows * op.ol[j].pitch;
+        }
+        int map_ints = 0;
+        for (int j = j0; j < J; ++j) {
+            int rows = 0;
+            for (int q = 0; q < parts; ++q) rows = std::max(rows, op.ol[j].c1[q] - op.ol[j].c0[q]);
+            op.ol[j].map_off = map_ints;
+            map_ints += 2 * rows + L + 2 * p.lv[j].Wo + L;
+        }
+        op.map_ints = (map_ints + 3) / 4 * 4;
+        if (((size_t)op.ring_floats + op.map_ints + floats) * 4 > kOwnerSmemMax) continue;
+        op.j0 = j0;
+        for (int j = j0; j < J; ++j) {
+            // segments sized so that one pass of the CTA's threads covers the part
+            int rows = 0;
+            for (int q = 0; q < parts; ++q) rows = std::max(rows, op.ol[j].c1[q] - op.ol[j].c0[q]);
+            const int ncpA = std::max(1, op.p.lv[j].ncpA);
+            const int rmin = std::max(2, H2 - 1);
+            // some warps are kept free for the border positions (about four rounds of them), which then run
+            // beside the interior segments instead of after them
+            const int itemsB = rows * (p.lv[j].Wo - 2 * op.p.lv[j].ncpA);
+            int spare = itemsB > 0 ? std::min(NT / 2, std::max(32, (ceil_div(itemsB, 4) + 31) & ~31)) : 0;
+            if ((NT - spare) / ncpA < 1) spare = 0;
+            const int rmax = std::max(16, 4 * (H2 - 1));
+            int R = std::max(rmin, ceil_div(rows, std::max(1, (NT - spare) / ncpA)));
+            if (R > rmax) R = std::max(rmin, ceil_div(rows, std::max(1, NT / ncpA)));   // no room: one class after the other
+            R = std::min(R, rmax);
+            if (stream_rows_override() > 0) R = stream_rows_override();
+            op.ol[j].R = std::max(1, std::min(R, rows));
+        }
+        return true;
+    }
+    return false;
+}
+
+template <int L, int S>
+static int launch_afb_owner_t(const AfbOwnerParams& op, cudaStream_t st) {
+    constexpr int NT = AfbOwnerCfg<L>::NT;
+    size_t floats = (size_t)op.ring_floats + op.map_ints;
+    for (int j = op.j0; j < op.p.J - 1; ++j) {
+        int rows = 0;
+        for (int q = 0; q < op.parts; ++q) rows = std::max(rows, op.ol[j].c1[q] - op.ol[j].c0[q]);
+        floats = std::max(floats, (size_t)op.ring_floats + op.map_ints + op.ol[j].buf_off + (size_t)rows * op.ol[j].pitch);
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        const cudaError_t e = cudaFuncSetAttribute(afb_owner_kernel<L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)kOwnerSmemMax);
+        if (e != cudaSuccess) return set_last_cuda_error(e);
+        attr_set = true;
+    }
+#ifdef B200W_TIMELINE
+    static unsigned long long* tl = nullptr;
+    const char* tl_path = getenv("B200W_TIMELINE_FILE");
+    const size_t ncta = (size_t)op.p.planes * op.parts;
+    if (tl_path && ncta <= 65536) {
+        if (!tl) cudaMalloc(&tl, sizeof(unsigned long long) * 16 * 65536);
+        cudaMemsetAsync(tl, 0, sizeof(unsigned long long) * 16 * 65536, st);
+        cudaMemcpyToSymbolAsync(g_timeline, &tl, sizeof(tl), 0, cudaMemcpyHostToDevice, st);
+    }
+#endif
+    afb_owner_kernel<L, S><<<(unsigned)(op.p.planes * op.parts), NT, floats * 4, st>>>(op);
+    const cudaError_t e = cudaGetLastError();
+#ifdef B200W_TIMELINE
+    if (tl_path && ncta <= 65536) {
+        cudaStreamSynchronize(st);
+        static unsigned long long host[16 * 65536];
+        cudaMemcpy(host, tl, sizeof(unsigned long long) * 16 * ncta, cudaMemcpyDeviceToHost);
+        FILE* f = fopen(tl_path, "wb");
+        if (f) { fwrite(host, sizeof(unsigned long long) * 16, ncta, f); fclose(f); }
+    }
+#endif
+    return e == cudaSuccess ? B200W_OK : set_last_cuda_error(e);
+}
+
+#define B200W_FOR_EACH_L(X) \
+    switch (L) {             \
+        case 2: X(2);        \
+        case 4: X(4);        \
+        case 6: X(6);        \
+        case 8: X(8);        \
+        case 10: X(10);      \
+        case 12: X(12);      \
+        case 14: X(14);      \
+        case 16: X(16);      \
+        default: break;      \
+    }
+
+bool afb_owner_plan(const AfbParams& p, int L, int sms, int j0_min, bool force, AfbOwnerParams& op) {
+    if (!afb_stream_supported(p, L)) return false;
+    const bool per = p.mode == B200W_MODE_PERIODIZATION;
+#define X(LL) return per ? afb_owner_plan_t<LL, afb_shift(LL, true)>(p, sms, j0_min, force, op) \
+                         : afb_owner_plan_t<LL, afb_shift(LL, false)>(p, sms, j0_min, force, op)
+    B200W_FOR_EACH_L(X)
+#undef X
+    return false;
+}
+
+int launch_afb_owner(const AfbOwnerParams& op, int L, cudaStream_t st) {
+    const bool per = op.p.mode == B200W_MODE_PERIODIZATION;
+#define X(LL) return per ? launch_afb_owner_t<LL, afb_shift(LL, true)>(op, st) \
+                         : launch_afb_owner_t<LL, afb_shift(LL, false)>(op, st)
+    B200W_FOR_EACH_L(X)
+#undef X
+    return B200W_ERR_BAD_TAPS;
 }
 
 int launch_afb_stream(AfbParams& p, int L, int sms, cudaStream_t st) {

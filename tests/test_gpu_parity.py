@@ -371,16 +371,22 @@ def test_host_pipeline_matches_direct_call():
         assert rel_err(dx, dx_ref.detach().cpu()) < 1e-6
 
 
-@pytest.mark.parametrize("env", ["B200W_FORCE_TILED", "B200W_PLANE", "B200W_FORCE_DIRECT"])
+@pytest.mark.parametrize("env", ["B200W_FORCE_TILED=1", "B200W_PLANE=1", "B200W_FORCE_DIRECT=1", "B200W_OWNER=2",
+                                 "B200W_OWNER=2 B200W_OWNER_J0=1", "B200W_OWNER=0"])
 def test_alternative_kernel_paths(env):
     """The same golden / oracle cases through the other implementations of the path (the env switches are read
-    once per process, hence a child pytest): shared-memory tile kernels, plane-resident kernels, direct kernels."""
+    once per process, hence a child pytest): shared-memory tile kernels, plane-resident kernels, direct kernels,
+    the owner kernel forced onto every multi-level shape that fits (also starting at level 1 behind a chain
+    launch), and the ticketed chain kernels alone."""
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     child_env = dict(os.environ)
-    child_env[env] = "1"
+    for kv in env.split():
+        k, v = kv.split("=")
+        child_env[k] = v
     res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-x",
-                          "-m", "gpu", "-k", "golden_dwt or golden_idwt or oracle_dwt_roundtrip or commutativity",
+                          "-m", "gpu", "-k", "golden_dwt or golden_idwt or oracle_dwt_roundtrip or commutativity or "
+                          "owner_kernel",
                           "-p", "no:cacheprovider"],
                          cwd=root, env=child_env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
                          timeout=1500)
@@ -545,3 +551,33 @@ def test_patch_model_swaps_the_discriminator_methods():
     case = [c for c in FSD_CASES if c["variant"] == "A" and c["cs"] == "sum"][0]
     got, x = mod.FS_DiscriminatorA("sum").to(DEV).filter_wavelet(cu(case["x"]), case["norm"])
     assert rel_err(got.cpu(), case["y"][0]) < RTOL_F32
+
+
+@pytest.mark.parametrize("shape,wave,mode,J", [((64, 1, 76, 76), "db3", "symmetric", 3),
+                                               ((160, 1, 50, 66), "db2", "reflect", 2),
+                                               ((40, 2, 75, 83), "haar", "zero", 4),
+                                               ((80, 1, 64, 96), "db4", "periodization", 3),
+                                               ((37, 2, 61, 47), "db5", "periodic", 2),
+                                               ((64, 1, 304, 304), "db3", "symmetric", 3)])
+def test_owner_kernel_shapes(shape, wave, mode, J):
+    """Shapes the default policy hands to the owner kernel (many small planes, J > 1; parts of a plane overlap by the
+    rows the deeper levels need) against the oracle, forward and gradient."""
+    rng = np.random.default_rng(J * 100 + shape[-1])
+    xn = rng.standard_normal(shape).astype(np.float32)
+    xfm = b200wave.DWTForward(J=J, wave=wave, mode=mode).to(DEV)
+    h = (xfm.h0_col.flatten().cpu().numpy().astype(np.float64), xfm.h1_col.flatten().cpu().numpy().astype(np.float64))
+    yl_o, yh_o = dwt_oracle.dwt_forward(xn.astype(np.float64), J, h, h, mode)
+    x = cu(xn, grad=True)
+    yl, yh = xfm(x)
+    assert rel_err(yl.detach().cpu(), yl_o) < RTOL_F32
+    for a, b in zip(yh, yh_o):
+        assert rel_err(a.detach().cpu(), b) < RTOL_F32
+    # gradient: the reference's AFB2D.backward chain, level by level
+    gl = rng.standard_normal(yl_o.shape).astype(np.float32)
+    gh = [rng.standard_normal(b.shape).astype(np.float32) for b in yh_o]
+    (dx,) = torch.autograd.grad([yl] + list(yh), x, [cu(gl)] + [cu(g) for g in gh])
+    d = gl.astype(np.float64)
+    sizes = [xn.shape[-2:]] + [b.shape[-2:] for b in yh_o[:-1]]
+    for j in range(J - 1, -1, -1):
+        d = dwt_oracle.afb2d_backward(d, gh[j].astype(np.float64), h[0], h[1], h[0], h[1], mode, sizes[j])
+    assert rel_err(dx.cpu(), d) < RTOL_F32

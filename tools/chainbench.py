@@ -37,7 +37,13 @@ def case(n, h, w, wave, mode, J):
         by / ts / 1e9 / PEAK * 100), flush=True)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "cfg2":
+    case(64, 304, 304, "db3", "symmetric", 3)
+    case(64, 304, 304, "db3", "symmetric", 2)
+    case(64, 154, 154, "db3", "symmetric", 2)
+    case(64, 304, 304, "haar", "zero", 3)
+    case(256, 128, 128, "db2", "reflect", 3)
+elif __name__ == "__main__":
     case(64, 304, 304, "db3", "symmetric", 1)
     case(64, 304, 304, "db3", "symmetric", 2)
     case(64, 304, 304, "db3", "symmetric", 3)
