@@ -1106,6 +1106,10 @@ static int run_sfb_chain(const float* yl, int64_t yl_ps, int64_t yl_rs, const fl
     if (templated_taps(Lw, Lh)) {
         // the coarse levels whose planes fit in shared memory run plane-resident (one launch), the finer ones after
         // them through the stream chain (or the tile chain)
+        if (J > 1 && !force_tiled() && owner_mode() != 0) {
+            SfbOwnerParams op;
+            if (sfb_owner_plan(p, Lw, device_info().sms, owner_mode() == 2, op)) return launch_sfb_owner(op, Lw, st);
+        }
         const int count = (force_tiled() || no_plane()) ? 0 : sfb_plane_count(p, Lw);
         if (count > 0) {
             rc = launch_sfb_plane(p, Lw, count, st);

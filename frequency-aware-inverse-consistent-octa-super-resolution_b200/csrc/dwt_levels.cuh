@@ -125,6 +125,14 @@ struct SfbParams {
     Taps t;
 };
 
+struct SfbOwnerParams {
+    SfbParams p;
+    OwnerLevel ol[kMaxLevels];   // per chain position: c0/c1 = output rows a part computes (h0/h1 the same)
+    int parts;
+    int ring_floats;       // size of the staging rings that precede the output images
+    int y_floats;          // size of the output images of all positions but the last
+};
+
 // launchers of the stream kernels (dwt_stream_afb.cu / dwt_stream_sfb.cu); the level geometry is complete
 // except for the stream work decomposition, which they fill in.  `sms` = SM count of the current device.
 bool afb_stream_supported(const AfbParams& p, int L);
@@ -137,6 +145,11 @@ int launch_sfb_stream(SfbParams& p, int L, int sms, cudaStream_t st);
 // memory, enough planes x parts to occupy the device -- unless `force`); j0_min = first level it may start from.
 bool afb_owner_plan(const AfbParams& p, int L, int sms, int j0_min, bool force, AfbOwnerParams& op);
 int launch_afb_owner(const AfbOwnerParams& op, int L, cudaStream_t st);
+
+// synthesis owner kernel (dwt_stream_sfb.cu): all positions of a synthesis chain in one launch, the intermediate
+// outputs in shared memory
+bool sfb_owner_plan(const SfbParams& p, int L, int sms, bool force, SfbOwnerParams& op);
+int launch_sfb_owner(const SfbOwnerParams& op, int L, cudaStream_t st);
 
 // plane-resident kernels (dwt_plane.cu): one CTA per plane runs the small levels of a transform in shared memory.
 // afb_plane_first = first analysis level from which on the rest fits (p.J = none); sfb_plane_count = number of

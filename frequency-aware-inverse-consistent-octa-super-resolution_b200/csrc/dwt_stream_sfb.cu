@@ -70,23 +70,46 @@ __device__ __forceinline__ void sfb_chain_wait(const unsigned* ctr, unsigned nee
     }
 }
 
+// rows of a chain position that an owner CTA works on (owner kernel only): it computes output rows [n0, n1) -- into
+// its shared-memory image of the level output, or into global memory at the last position
+struct SfbOwnRows {
+    int n0, n1;
+    int itemsA;            // thread items of the interior class over those rows
+    unsigned low_s;        // SMEM_LOW: shared address of the low-pass image (row low_row0, column 0)
+    int low_row0;
+};
+
+__device__ __forceinline__ float2 lds64(unsigned addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds32(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
 // ---- interior threads: per-warp cp.async ring ----------------------------------------------------------
-template <int L, int V, int S2>
-__device__ __forceinline__ void sfb_ring_cta(const SfbParams& p, const SfbLevel& lv, int plane, int cta, float2* ring_all,
-                                             const unsigned* wait_ctr, unsigned wait_need) {
+// `it` = the thread's item (segment-major: segment * ntA + interior thread).  OWNER: the rows come from `own`
+// instead of the whole level; SMEM_LOW (owner kernel, every position but the first): the low-pass input is the
+// previous position's output in shared memory -- only the three detail bands go through the ring.
+template <int L, int V, int S2, bool OWNER = false, bool SMEM_LOW = false>
+__device__ __forceinline__ void sfb_ring_cta(const SfbParams& p, const SfbLevel& lv, int plane, int it, float2* ring_all,
+                                             const unsigned* wait_ctr, unsigned wait_need, const SfbOwnRows& own) {
     using C = SfbStreamCfg<L, S2>;
     constexpr int H2 = C::H2, NCF = C::NCF, NS = C::NS, D = C::D;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int it = cta * kStreamNT + tid;
-    const bool active = it < lv.itemsA;
+    const int itemsA = OWNER ? own.itemsA : lv.itemsA;
+    const bool active = it < itemsA;
     const int ntA = lv.ntA;
-    const int itc = active ? it : lv.itemsA - 1;     // inactive lanes shadow the last item (no copies, no stores)
+    const int itc = active ? it : itemsA - 1;        // inactive lanes shadow the last item (no copies, no stores)
     const int seg = itc / ntA;
     const int tl = itc - seg * ntA;
     const int t = lv.tA0 + tl;
-    const int m0 = lv.m_lo + seg * lv.Rp;                            // first output row pair (A-space)
-    const int m_end = ((lv.offH + lv.out_h - 1) >> 1) + 1;
+    const int m0 = (OWNER ? (own.n0 + lv.offH) >> 1 : lv.m_lo) + seg * lv.Rp;   // first output row pair (A-space)
+    const int m_end = ((lv.offH + (OWNER ? own.n1 : lv.out_h) - 1) >> 1) + 1;
     const int nm = min(lv.Rp, m_end - m0);
     const int nrows = active ? nm + H2 - 1 : 0;                      // coefficient rows feeding them
     const int kr0 = m0 - (H2 - 1);
@@ -112,7 +135,7 @@ __device__ __forceinline__ void sfb_ring_cta(const SfbParams& p, const SfbLevel&
         if (q < nrows) {
             const int sr = sfb_src_row(kr0 + q, h, periodic);
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
+            for (int b = SMEM_LOW ? 1 : 0; b < 4; ++b) {
                 const unsigned dst = ring_s + (unsigned)((st * 4 + b) * C::RPB) * 8u;
                 if (sr >= 0 && (b == 0 || has_hi)) {
                     const float* src = b == 0 ? lowcol + (long long)sr * low_rs : hicol + (size_t)(b - 1) * band + (size_t)sr * w;
@@ -142,7 +165,7 @@ __device__ __forceinline__ void sfb_ring_cta(const SfbParams& p, const SfbLevel&
         }
     };
 
-    const int out_h = lv.out_h;
+    const int row_lo = OWNER ? own.n0 : 0, row_hi = OWNER ? own.n1 : lv.out_h;
     const int n0 = 4 * t + lv.n0_off;                                // first output column (all four are valid)
     const long long y_rs = lv.y_rs;
     int nrow = 2 * m0 - lv.offH;                                     // output row of the even row of pair m0
@@ -154,12 +177,14 @@ __device__ __forceinline__ void sfb_ring_cta(const SfbParams& p, const SfbLevel&
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) npw = max(npw, __shfl_xor_sync(0xffffffffu, npw, o));
 
-    sfb_chain_wait(wait_ctr, wait_need);
+    if (!OWNER) sfb_chain_wait(wait_ctr, wait_need);
 #pragma unroll 1
     for (int s = 0; s < D - 1; ++s) {
         issue(s, s);
         cp_async_commit();
     }
+    // SMEM_LOW: shared address of this lane's low-pass window in row 0
+    const unsigned loww_s = SMEM_LOW ? own.low_s + (unsigned)(kb - own.low_row0 * (int)low_rs) * 4u : 0u;
     float2 acc[H2][4];    // ring of pending output row pairs: even row (cols 0-1, 2-3), odd row (cols 0-1, 2-3)
     int st_r = 0, st_w = D - 1;
     // long filters keep the accumulator ring in age order and shift it after each store instead of unrolling by
@@ -179,13 +204,31 @@ __device__ __forceinline__ void sfb_ring_cta(const SfbParams& p, const SfbLevel&
                 float c[4][NCF];
                 const float2* src = ring + (st_r * 4) * C::RPB + slot;
 #pragma unroll
-                for (int b = 0; b < 4; ++b)
+                for (int b = SMEM_LOW ? 1 : 0; b < 4; ++b)
 #pragma unroll
                     for (int k = 0; k < NS; ++k) {
                         const float2 v = src[b * C::RPB + k];
                         c[b][2 * k] = v.x;
                         c[b][2 * k + 1] = v.y;
                     }
+                if (SMEM_LOW) {
+                    const int sr = q < nrows ? sfb_src_row(kr0 + q, h, periodic) : -1;
+                    const unsigned a = loww_s + (unsigned)(max(sr, 0) * (int)low_rs) * 4u;
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) {
+                        float2 v = make_float2(0.f, 0.f);
+                        if (sr >= 0) {
+                            if (V == 2) {
+                                v = lds64(a + 8u * k);
+                            } else {
+                                v.x = lds32(a + 8u * k);
+                                v.y = lds32(a + 8u * k + 4u);
+                            }
+                        }
+                        c[0][2 * k] = v.x;
+                        c[0][2 * k + 1] = v.y;
+                    }
+                }
                 // W synthesis of this coefficient row: lo = h_lo branch (LL, HL), hi = h_hi branch (LH, HH)
                 float lo[4], hi[4];
 #pragma unroll
@@ -230,7 +273,7 @@ __device__ __forceinline__ void sfb_ring_cta(const SfbParams& p, const SfbLevel&
 #pragma unroll
                     for (int r = 0; r < 2; ++r) {
                         const int row = nrow + r;
-                        if (row >= 0 && row < out_h) {
+                        if (row >= row_lo && row < row_hi) {
                             float* d = yq + r * y_rs;
                             if (yv == 4) {
                                 *reinterpret_cast<float4*>(d) = make_float4(s[2 * r].x, s[2 * r].y, s[2 * r + 1].x, s[2 * r + 1].y);
@@ -261,14 +304,15 @@ __device__ __forceinline__ void sfb_ring_cta(const SfbParams& p, const SfbLevel&
 // ---- border output columns: one thread per output position ---------------------------------------------
 // All (L/2)^2 x 4 coefficients of an output are loaded before any arithmetic (clamped address + select), so the
 // thread pays one memory round trip; rows are done in chunks to bound the registers.
-template <int L>
+template <int L, bool OWNER = false>
 __device__ __forceinline__ void sfb_border_item(const SfbParams& p, const SfbLevel& lv, int plane, int it, bool active,
-                                                const unsigned* wait_ctr, unsigned wait_need) {
+                                                const unsigned* wait_ctr, unsigned wait_need, const SfbOwnRows& own) {
     constexpr int H2 = L / 2;
     if (!active) it = 0;                             // idle threads shadow item 0 (they only take part in the wait)
     const int ncB = lv.nA0 + lv.out_w - lv.nA1;      // border columns per output row
-    const int nH = it / ncB;
-    const int e0 = it - nH * ncB;
+    const int ib = it / ncB;
+    const int nH = (OWNER ? own.n0 : 0) + ib;
+    const int e0 = it - ib * ncB;
     const int nW = e0 < lv.nA0 ? e0 : e0 - lv.nA0 + lv.nA1;
     const int h = lv.h, w = lv.w, periodic = p.periodic;
     const size_t band = (size_t)h * w;
@@ -286,7 +330,7 @@ __device__ __forceinline__ void sfb_border_item(const SfbParams& p, const SfbLev
     int krow[H2];
 #pragma unroll
     for (int u = 0; u < H2; ++u) krow[u] = sfb_src_row((AH >> 1) - u, h, periodic);
-    sfb_chain_wait(wait_ctr, wait_need);             // index arithmetic above overlaps the wait
+    if (!OWNER) sfb_chain_wait(wait_ctr, wait_need); // index arithmetic above overlaps the wait
     if (!active) return;
     float y = 0.f;
     constexpr int CH = H2 < 3 ? H2 : 3;
@@ -354,16 +398,82 @@ __global__ void __launch_bounds__(kStreamNT, SfbStreamCfg<L, S2V>::MINB) sfb_str
     // the previous (coarser) level of this plane must be complete before its output is read as `low`
     const unsigned* wait_ctr = level > 0 ? p.done + (size_t)(level - 1) * p.planes + plane : nullptr;
     const unsigned wait_need = level > 0 ? (unsigned)p.lv[level - 1].cpp : 0u;
+    const SfbOwnRows none{};
     if (cta < lv.cppA) {
-        if (lv.vec2) sfb_ring_cta<L, 2, S2V>(p, lv, plane, cta, sfb_ring_all, wait_ctr, wait_need);
-        else sfb_ring_cta<L, 1, 0>(p, lv, plane, cta, sfb_ring_all, wait_ctr, wait_need);
+        const int it = cta * kStreamNT + tid;
+        if (lv.vec2) sfb_ring_cta<L, 2, S2V>(p, lv, plane, it, sfb_ring_all, wait_ctr, wait_need, none);
+        else sfb_ring_cta<L, 1, 0>(p, lv, plane, it, sfb_ring_all, wait_ctr, wait_need, none);
     } else {
         const int it = (cta - lv.cppA) * kStreamNT + tid;
-        sfb_border_item<L>(p, lv, plane, it, it < lv.itemsB, wait_ctr, wait_need);
+        sfb_border_item<L>(p, lv, plane, it, it < lv.itemsB, wait_ctr, wait_need, none);
     }
     if (level + 1 < p.J) {
         __syncthreads();
         if (tid == 0) signal_done(p.done + (size_t)level * p.planes + plane);
+    }
+}
+
+// ---- owner kernel: every position of a synthesis chain for one (plane, part) in one CTA ------------------------
+// The coarsest position reads its low-pass input from global memory through the ring like the stream kernel; every
+// output but the last stays in shared memory, where the next position reads it as its low-pass input (SMEM_LOW),
+// the detail bands still streaming in through the ring.  One block barrier per position, no tickets or counters.
+template <int L>
+struct SfbOwnerCfg {
+    static constexpr int NT = L <= 8 ? 512 : 256;   // one CTA per SM; long filters need > 128 registers per thread
+};
+
+template <int L, int S2V>
+__global__ void __launch_bounds__(SfbOwnerCfg<L>::NT, 1) sfb_owner_kernel(const __grid_constant__ SfbOwnerParams op) {
+    extern __shared__ float2 sfb_ring_all[];
+    constexpr int NT = SfbOwnerCfg<L>::NT;
+    const SfbParams& p = op.p;
+    const int tid = threadIdx.x;
+    const int plane = blockIdx.x / op.parts;
+    const int part = blockIdx.x - plane * op.parts;
+    float* const y_area = reinterpret_cast<float*>(sfb_ring_all) + op.ring_floats;
+#pragma unroll 1
+    for (int c = 0; c < p.J; ++c) {
+        SfbLevel lv = p.lv[c];
+        const OwnerLevel& ol = op.ol[c];
+        SfbOwnRows own;
+        own.n0 = ol.c0[part];
+        own.n1 = ol.c1[part];
+        own.low_s = 0;
+        own.low_row0 = 0;
+        const bool smem_low = c > 0;
+        if (smem_low) {   // low-pass input = the previous position's output rows in shared memory
+            const OwnerLevel& pv = op.ol[c - 1];
+            float* buf = y_area + pv.buf_off;
+            own.low_s = (unsigned)__cvta_generic_to_shared(buf);
+            own.low_row0 = pv.c0[part];
+            lv.low = buf - (long long)pv.c0[part] * pv.pitch;   // generic pointer for the border items
+            lv.low_ps = 0;
+            lv.low_rs = pv.pitch;
+        }
+        if (c + 1 < p.J) {   // the output stays on chip
+            lv.y = y_area + ol.buf_off - (long long)own.n0 * ol.pitch;
+            lv.y_ps = 0;
+            lv.y_rs = ol.pitch;
+        }
+        lv.Rp = ol.R;
+        const int npairs = ((lv.offH + own.n1 - 1) >> 1) + 1 - ((own.n0 + lv.offH) >> 1);
+        own.itemsA = ((npairs + lv.Rp - 1) / lv.Rp) * lv.ntA;
+        for (int base = 0; base < own.itemsA; base += NT) {
+            __syncwarp();   // the warp's ring is reused from pass to pass
+            const int it = base + tid;
+            if (smem_low) {
+                if (lv.vec2) sfb_ring_cta<L, 2, S2V, true, true>(p, lv, plane, it, sfb_ring_all, nullptr, 0u, own);
+                else sfb_ring_cta<L, 1, 0, true, true>(p, lv, plane, it, sfb_ring_all, nullptr, 0u, own);
+            } else {
+                if (lv.vec2) sfb_ring_cta<L, 2, S2V, true, false>(p, lv, plane, it, sfb_ring_all, nullptr, 0u, own);
+                else sfb_ring_cta<L, 1, 0, true, false>(p, lv, plane, it, sfb_ring_all, nullptr, 0u, own);
+            }
+        }
+        // border columns go to the last threads first: warps with no or short segments start them early
+        const int itemsB = (own.n1 - own.n0) * (lv.nA0 + lv.out_w - lv.nA1);
+        for (int it = NT - 1 - tid; it < itemsB; it += NT)
+            sfb_border_item<L, true>(p, lv, plane, it, true, nullptr, 0u, own);
+        __syncthreads();   // this position's output is complete before the next one reads it
     }
 }
 
@@ -387,6 +497,164 @@ bool sfb_stream_supported(const SfbParams& p, int L) {
     return true;
 }
 
+// interior / border split of the output columns of a level and the staging geometry (stream and owner kernels)
+template <int L, bool PER>
+static void sfb_stream_columns(SfbLevel& lv) {
+    constexpr int S2V = sfb_shift2(L, PER);
+    using CV = SfbStreamCfg<L, S2V>;
+    using C1 = SfbStreamCfg<L, 0>;
+    lv.vec2 = (!(lv.low_rs & 1) && !(lv.low_ps & 1) && aligned_to(lv.low, 8) &&
+               (!lv.highs || (!(lv.w & 1) && aligned_to(lv.highs, 8)))) ? 1 : 0;
+    const int ncf = lv.vec2 ? CV::NCF : C1::NCF;
+    lv.n0_off = sfb_n0_off(L, PER);
+    lv.kb_off = lv.vec2 ? sfb_ks_off(L, PER) - S2V : sfb_ks_off(L, PER);
+    lv.m_lo = lv.offH >> 1;
+    // interior threads: window [kb, kb+ncf) inside [0, w) and outputs n0 .. n0+3 inside [0, out_w)
+    int t0 = lv.kb_off < 0 ? (-lv.kb_off + 1) / 2 : 0;
+    if (lv.n0_off < 0 && t0 < 1) t0 = 1;
+    int t1 = lv.w - ncf - lv.kb_off >= 0 ? (lv.w - ncf - lv.kb_off) / 2 + 1 : 0;
+    const int t1o = lv.out_w - 4 - lv.n0_off >= 0 ? (lv.out_w - 4 - lv.n0_off) / 4 + 1 : 0;
+    t1 = std::min(t1, t1o);
+    lv.tA0 = t0;
+    lv.ntA = t1 - t0;
+    if (lv.ntA < kSfbMinThreads) lv.ntA = 0;   // too narrow for the ring: every column takes the border path
+    lv.nA0 = lv.ntA > 0 ? 4 * lv.tA0 + lv.n0_off : lv.out_w;
+    lv.nA1 = lv.ntA > 0 ? 4 * (lv.tA0 + lv.ntA) + lv.n0_off : lv.out_w;
+    lv.y_vec = 1;
+    if (lv.n0_off == 0 && !(lv.y_rs & 1) && !(lv.y_ps & 1) && aligned_to(lv.y, 8)) lv.y_vec = 2;
+    if (lv.y_vec == 2 && !(lv.y_rs & 3) && !(lv.y_ps & 3) && aligned_to(lv.y, 16)) lv.y_vec = 4;
+}
+
+constexpr size_t kSfbOwnerSmemMax = 227 * 1024;
+
+template <int L, bool PER>
+static bool sfb_owner_plan_t(const SfbParams& p, int sms, bool force, SfbOwnerParams& op) {
+    constexpr int NT = SfbOwnerCfg<L>::NT;
+    constexpr int H2 = L / 2;
+    const int J = p.J;
+    if (J < 2) return false;
+    int parts = std::min(kMaxParts, std::max(1, sms / p.planes));
+    if (PER) parts = 1;   // the coefficient rows wrap around: a part would need rows from the far end
+    parts = std::min(parts, p.lv[J - 1].out_h);
+    if (!force && (long long)p.planes * parts < sms / 2) return false;
+    op.p = p;
+    op.parts = parts;
+    // ring of the staging variants this launch can use (64-bit copies with the mode's shift, or 32-bit copies)
+    constexpr size_t ring128 = std::max(SfbStreamCfg<L, sfb_shift2(L, PER)>::smem, SfbStreamCfg<L, 0>::smem);
+    op.ring_floats = (int)(ring128 / kStreamNT * NT / 4);
+    // rows: the last position's output rows are split evenly over the parts; every earlier position computes the
+    // rows the next one reads as low-pass coefficients
+    for (int q = 0; q < parts; ++q) {
+        op.ol[J - 1].c0[q] = (int)((long long)p.lv[J - 1].out_h * q / parts);
+        op.ol[J - 1].c1[q] = (int)((long long)p.lv[J - 1].out_h * (q + 1) / parts);
+        for (int c = J - 2; c >= 0; --c) {
+            const SfbLevel& nx = p.lv[c + 1];
+            int lo = ((op.ol[c + 1].c0[q] + nx.offH) >> 1) - (H2 - 1);
+            int hi = ((op.ol[c + 1].c1[q] - 1 + nx.offH) >> 1) + 1;
+            if (PER) {
+                lo = 0;
+                hi = nx.h;
+            }
+            lo = std::max(lo, 0);
+            hi = std::min(hi, nx.h);
+            if (hi <= lo) {   // nothing of this output is read (degenerate crop): keep one row so that sizes stay positive
+                lo = std::min(lo, nx.h - 1);
+                lo = std::max(lo, 0);
+                hi = lo + 1;
+            }
+            op.ol[c].c0[q] = lo;
+            op.ol[c].c1[q] = hi;
+        }
+    }
+    size_t floats = 0;
+    for (int c = 0; c < J; ++c) {
+        SfbLevel& lv = op.p.lv[c];
+        OwnerLevel& ol = op.ol[c];
+        int rows = 0;
+        for (int q = 0; q < parts; ++q) {
+            rows = std::max(rows, ol.c1[q] - ol.c0[q]);
+            ol.h0[q] = ol.c0[q];
+            ol.h1[q] = ol.c1[q];
+        }
+        ol.map_off = 0;
+        if (c + 1 < J) {   // output image in shared memory: 16-byte aligned rows
+            ol.pitch = (lv.out_w + 3) / 4 * 4;
+            ol.buf_off = (int)floats;
+            floats += (size_t)rows * ol.pitch;
+            lv.y_rs = ol.pitch;
+            lv.y_ps = 0;
+        } else {
+            ol.pitch = 0;
+            ol.buf_off = 0;
+        }
+        if (c > 0) {       // low-pass input = that image: even pitch, aligned base
+            lv.low_rs = op.ol[c - 1].pitch;
+            lv.low_ps = 0;
+        }
+        // geometry with the shared-memory strides; the alignment tests on lv.low / lv.y must see aligned pointers
+        const float* low_keep = lv.low;
+        float* y_keep = lv.y;
+        if (c > 0) lv.low = nullptr;
+        if (c + 1 < J) lv.y = nullptr;
+        sfb_stream_columns<L, PER>(lv);
+        lv.low = low_keep;
+        lv.y = y_keep;
+        const int npairs = ((lv.offH + rows - 1) >> 1) + 2;   // upper bound over the parts' row offsets
+        const int ntA = std::max(1, lv.ntA);
+        int Rp = std::max(std::max(2, H2 - 1), ceil_div(npairs, std::max(1, NT / ntA)));
+        Rp = std::min(Rp, std::max(16, 4 * (H2 - 1)));
+        if (stream_pairs_override() > 0) Rp = stream_pairs_override();
+        ol.R = std::max(1, Rp);
+    }
+    op.y_floats = (int)floats;
+    return ((size_t)op.ring_floats + floats) * 4 <= kSfbOwnerSmemMax;
+}
+
+template <int L, bool PER>
+static int launch_sfb_owner_t(const SfbOwnerParams& op, cudaStream_t st) {
+    constexpr int NT = SfbOwnerCfg<L>::NT;
+    constexpr int S2V = sfb_shift2(L, PER);
+    static bool attr_set = false;
+    if (!attr_set) {
+        const cudaError_t e = cudaFuncSetAttribute(sfb_owner_kernel<L, S2V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)kSfbOwnerSmemMax);
+        if (e != cudaSuccess) return set_last_cuda_error(e);
+        attr_set = true;
+    }
+    const size_t smem = ((size_t)op.ring_floats + op.y_floats) * 4;
+    sfb_owner_kernel<L, S2V><<<(unsigned)(op.p.planes * op.parts), NT, smem, st>>>(op);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? B200W_OK : set_last_cuda_error(e);
+}
+
+#define B200W_SFB_FOR_EACH_L(X) \
+    switch (L) {                 \
+        case 2: X(2);            \
+        case 4: X(4);            \
+        case 6: X(6);            \
+        case 8: X(8);            \
+        case 10: X(10);          \
+        case 12: X(12);          \
+        case 14: X(14);          \
+        case 16: X(16);          \
+        default: break;          \
+    }
+
+bool sfb_owner_plan(const SfbParams& p, int L, int sms, bool force, SfbOwnerParams& op) {
+    if (!sfb_stream_supported(p, L)) return false;
+#define X(LL) return p.periodic ? sfb_owner_plan_t<LL, true>(p, sms, force, op) : sfb_owner_plan_t<LL, false>(p, sms, force, op)
+    B200W_SFB_FOR_EACH_L(X)
+#undef X
+    return false;
+}
+
+int launch_sfb_owner(const SfbOwnerParams& op, int L, cudaStream_t st) {
+#define X(LL) return op.p.periodic ? launch_sfb_owner_t<LL, true>(op, st) : launch_sfb_owner_t<LL, false>(op, st)
+    B200W_SFB_FOR_EACH_L(X)
+#undef X
+    return B200W_ERR_BAD_TAPS;
+}
+
 template <int L, bool PER>
 static int launch_sfb_stream_t(SfbParams& p, int sms, cudaStream_t st) {
     constexpr int H2 = L / 2;
@@ -400,23 +668,7 @@ static int launch_sfb_stream_t(SfbParams& p, int sms, cudaStream_t st) {
     long long base = 0;
     for (int j = 0; j < p.J; ++j) {
         SfbLevel& lv = p.lv[j];
-        lv.vec2 = (!(lv.low_rs & 1) && !(lv.low_ps & 1) && aligned_to(lv.low, 8) &&
-                   (!lv.highs || (!(lv.w & 1) && aligned_to(lv.highs, 8)))) ? 1 : 0;
-        const int ncf = lv.vec2 ? CV::NCF : C1::NCF;
-        lv.n0_off = sfb_n0_off(L, PER);
-        lv.kb_off = lv.vec2 ? sfb_ks_off(L, PER) - S2V : sfb_ks_off(L, PER);
-        lv.m_lo = lv.offH >> 1;
-        // interior threads: window [kb, kb+ncf) inside [0, w) and outputs n0 .. n0+3 inside [0, out_w)
-        int t0 = lv.kb_off < 0 ? (-lv.kb_off + 1) / 2 : 0;
-        if (lv.n0_off < 0 && t0 < 1) t0 = 1;
-        int t1 = lv.w - ncf - lv.kb_off >= 0 ? (lv.w - ncf - lv.kb_off) / 2 + 1 : 0;
-        const int t1o = lv.out_w - 4 - lv.n0_off >= 0 ? (lv.out_w - 4 - lv.n0_off) / 4 + 1 : 0;
-        t1 = std::min(t1, t1o);
-        lv.tA0 = t0;
-        lv.ntA = t1 - t0;
-        if (lv.ntA < kSfbMinThreads) lv.ntA = 0;   // too narrow for the ring: every column takes the border path
-        lv.nA0 = lv.ntA > 0 ? 4 * lv.tA0 + lv.n0_off : lv.out_w;
-        lv.nA1 = lv.ntA > 0 ? 4 * (lv.tA0 + lv.ntA) + lv.n0_off : lv.out_w;
+        sfb_stream_columns<L, PER>(lv);
         const int npairs = ((lv.offH + lv.out_h - 1) >> 1) + 1 - lv.m_lo;
         int Rp = rpref;
         if (j + 1 < p.J) {
@@ -431,9 +683,6 @@ static int launch_sfb_stream_t(SfbParams& p, int sms, cudaStream_t st) {
         lv.cppA = ceil_div(lv.itemsA, kStreamNT);
         lv.itemsB = lv.out_h * (lv.nA0 + lv.out_w - lv.nA1);
         lv.cpp = lv.cppA + ceil_div(lv.itemsB, kStreamNT);
-        lv.y_vec = 1;
-        if (lv.n0_off == 0 && !(lv.y_rs & 1) && !(lv.y_ps & 1) && aligned_to(lv.y, 8)) lv.y_vec = 2;
-        if (lv.y_vec == 2 && !(lv.y_rs & 3) && !(lv.y_ps & 3) && aligned_to(lv.y, 16)) lv.y_vec = 4;
         lv.cta_base = base;
         base += (long long)lv.cpp * p.planes;
     }

@@ -572,6 +572,14 @@ def test_owner_kernel_shapes(shape, wave, mode, J):
     assert rel_err(yl.detach().cpu(), yl_o) < RTOL_F32
     for a, b in zip(yh, yh_o):
         assert rel_err(a.detach().cpu(), b) < RTOL_F32
+    # synthesis chain on the same coefficients (owner kernel of the inverse transform)
+    ifm = b200wave.DWTInverse(wave=wave, mode=mode).to(DEV)
+    g = (ifm.g0_col.flatten().cpu().numpy().astype(np.float64), ifm.g1_col.flatten().cpu().numpy().astype(np.float64))
+    rec = ifm((yl.detach(), [t.detach() for t in yh]))
+    assert rel_err(rec.cpu(), dwt_oracle.dwt_inverse(yl_o, yh_o, g, g, mode)) < RTOL_F32
+    rec0 = ifm((yl.detach(), [None] * J))                    # detail bands absent = zeros (and no 'unpad' crops)
+    if rec0.shape == rec.shape:
+        assert rel_err(rec0.cpu(), dwt_oracle.dwt_inverse(yl_o, [np.zeros_like(t) for t in yh_o], g, g, mode)) < RTOL_F32
     # gradient: the reference's AFB2D.backward chain, level by level
     gl = rng.standard_normal(yl_o.shape).astype(np.float32)
     gh = [rng.standard_normal(b.shape).astype(np.float32) for b in yh_o]
