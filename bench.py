@@ -267,8 +267,7 @@ def main():
         L = xfm.h0_col.numel()
         passes = 4 if cfg["grad"] else 2
         step_bytes = passes * dwt_pass_bytes(cfg["shape"], L, cfg["J"], cfg["mode"]) + (8 * n * c * h * w if crit else 0)
-        # one chain kernel per multi-level transform (+ the kernel that clears its completion counters)
-        my_kernels_per_step = passes * (2 if cfg["J"] > 1 else 1) + (2 if crit else 0)
+        my_kernels_per_step = None   # counted below from the library's own launch counter
 
         def step(x, g):
             if cfg["grad"]:
@@ -291,7 +290,7 @@ def main():
     else:
         crit = b200wave.SSIM()
         step_bytes = 20 * n * c * h * w
-        my_kernels_per_step = 3
+        my_kernels_per_step = None
 
         def step(x, y):
             x.grad = None
@@ -312,6 +311,15 @@ def main():
     for i in range(max(3, min(args.warmup, nsets))):
         step(*sets[i % nsets])
     torch.cuda.synchronize()
+    # kernels of ours one step launches: the library counts its launches (b200w_kernel_launches) and names them
+    from b200wave import _cabi
+    before = _cabi.kernel_launches()
+    step(*sets[0])
+    torch.cuda.synchronize()
+    my_kernels_per_step = _cabi.kernel_launches() - before
+    step_kernels = _cabi.recent_kernels(my_kernels_per_step)
+    if my_kernels_per_step <= 0:
+        raise RuntimeError("the step launched none of the library's kernels: refusing to report a number")
 
     graphs = None
     if not args.no_graph:
@@ -449,11 +457,13 @@ def main():
                     # backward passes use the same two kernels)
                     chain_bytes = dwt_pass_bytes(cfg["shape"], L, cfg["J"], cfg["mode"])
                     t_dwt = time_kernel(lambda i: xfm(sets[i % nsets][0].detach()))
+                    k_dwt = _cabi.recent_kernels(1)[0]
                     t_idwt = time_kernel(lambda i: ifm(coeffs[i % nsets]))
+                    k_idwt = _cabi.recent_kernels(1)[0]
                     kernels["dwt2_chain"] = {"s": t_dwt, "GB/s": chain_bytes / t_dwt / 1e9, "bytes": chain_bytes,
-                                             "sass": "afb_stream_kernel", "levels": cfg["J"]}
+                                             "sass": k_dwt, "levels": cfg["J"]}
                     kernels["idwt2_chain"] = {"s": t_idwt, "GB/s": chain_bytes / t_idwt / 1e9, "bytes": chain_bytes,
-                                              "sass": "sfb_stream_kernel", "levels": cfg["J"]}
+                                              "sass": k_idwt, "levels": cfg["J"]}
                     name = "dwt2_chain" if t_dwt >= t_idwt else "idwt2_chain"
                 del coeffs
             else:
@@ -499,7 +509,7 @@ def main():
                     "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
                     "api": "b200wave.HostPipeline(step, chunks=%d): pinned host -> H2D | kernels | D2H overlapped "
                            "on three streams" % len(pipe.bounds)},
-            "gpu_launches": my_kernels_per_step * args.steps,
+            "gpu_launches": my_kernels_per_step * args.steps, "step_kernels": step_kernels,
             "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks,
         }
         if saved_stdout is not None:

@@ -47,6 +47,8 @@ SYMBOLS = {
     "b200w_afb2d_ex_f32": (_i, [_vp, _i64, _i64, _i, _i, _i,
                                 _c_float_p, _c_float_p, _i, _c_float_p, _c_float_p, _i,
                                 _i, _vp, _vp, ctypes.c_float, ctypes.c_float, _vp]),
+    "b200w_kernel_launches": (ctypes.c_ulonglong, []),
+    "b200w_kernel_log": (ctypes.c_char_p, [_i]),
     "b200w_dwt2_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i, _c_int_p]),
     "b200w_dwt2_f32": (_i, [_vp, _i64, _i64, _i, _i, _i,
                             _c_float_p, _c_float_p, _i, _c_float_p, _c_float_p, _i,
@@ -133,3 +135,14 @@ def check(code, mode_name=None):
     if code == ERR_LAUNCH:
         msg += " (cudaError %d)" % load().b200w_last_cuda_error()
     raise B200WaveError("b200wave: " + msg)
+
+
+def kernel_launches():
+    """Kernels launched by the library in this process so far."""
+    return int(load().b200w_kernel_launches())
+
+
+def recent_kernels(n):
+    """Names of the last ``n`` kernels launched, oldest first."""
+    lib = load()
+    return [lib.b200w_kernel_log(i).decode() for i in range(min(n, 64) - 1, -1, -1)]

@@ -1,13 +1,30 @@
 // ABI bookkeeping: version, status names, last CUDA error (thread-local, diagnostics only).
+#include <atomic>
 #include "common.cuh"
 
 namespace b200w {
+constexpr int kLaunchLog = 64;
 static thread_local int g_last_cuda_error = 0;
 int set_last_cuda_error(cudaError_t e) {
     g_last_cuda_error = (int)e;
     return B200W_ERR_LAUNCH;
 }
+static std::atomic<unsigned long long> g_launches{0};
+static const char* g_log[kLaunchLog] = {nullptr};
+void note_launch(const char* kernel) {
+    const unsigned long long n = g_launches.fetch_add(1, std::memory_order_relaxed);
+    g_log[n % kLaunchLog] = kernel;
+}
 }  // namespace b200w
+
+extern "C" unsigned long long b200w_kernel_launches(void) { return b200w::g_launches.load(std::memory_order_relaxed); }
+
+extern "C" const char* b200w_kernel_log(int back) {
+    const unsigned long long n = b200w::g_launches.load(std::memory_order_relaxed);
+    if (back < 0 || back >= b200w::kLaunchLog || (unsigned long long)back >= n) return "";
+    const char* s = b200w::g_log[(n - 1 - (unsigned long long)back) % b200w::kLaunchLog];
+    return s ? s : "";
+}
 
 extern "C" int b200w_abi_version(void) { return B200W_ABI_VERSION; }
 

@@ -119,5 +119,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 int set_last_cuda_error(cudaError_t e);
+// diagnostics: counts the launch and remembers the kernel's name (b200w_kernel_launches / b200w_kernel_log)
+void note_launch(const char* kernel);
 
 }  // namespace b200w

@@ -35,6 +35,7 @@ __global__ void zero_words_kernel(unsigned* w, unsigned n) {
 
 int zero_sync_words(unsigned* words, size_t n, cudaStream_t st) {
     zero_words_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(words, (unsigned)n);
+    note_launch("zero_words_kernel");
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? B200W_OK : set_last_cuda_error(e);
 }
@@ -212,6 +213,7 @@ __device__ __forceinline__ void stage_analysis(unsigned patch_s, const float* __
 template <int L_, int TW_, int TH_, int NT_>
 struct AfbOp {
     using Params = AfbParams;
+    static constexpr const char* name = "chain_kernel<AfbOp>";
     static constexpr int L = L_, TW = TW_, TH = TH_, NT = NT_;
     static constexpr int PC = 2 * TW + L - 2;     // staged patch columns actually needed
     static constexpr int PCP = (PC + 3) & ~3;     // row pitch (multiple of 4 floats: 128-bit LDS)
@@ -457,6 +459,7 @@ __device__ __forceinline__ void stage_synthesis(unsigned sub_s, const float* __r
 template <int L_, int TW_, int TH_, int NT_>
 struct SfbOp {
     using Params = SfbParams;
+    static constexpr const char* name = "chain_kernel<SfbOp>";
     static constexpr int L = L_, TW = TW_, TH = TH_, NT = NT_;
     static constexpr int H2 = L / 2;
     static constexpr int NV2 = (H2 + 2) / 2;            // float2 loads per band per W-synthesis item
@@ -783,6 +786,7 @@ static int launch_chain(typename Op::Params& p, int* occ_cache, cudaStream_t st)
         kernel<<<(unsigned)grid, Op::NT, Op::smem, st>>>(p);
         e = cudaGetLastError();
     }
+    note_launch(Op::name);
     return e == cudaSuccess ? B200W_OK : set_last_cuda_error(e);
 }
 
@@ -1000,6 +1004,7 @@ static int run_afb_chain(const float* x, int64_t x_ps, int64_t x_rs, int planes,
         d.Lh = Lh;
         d.t = p.t;
         afb2d_direct_kernel<<<(unsigned)direct_grid((size_t)planes * d.lv.Ho * d.lv.Wo), kThreads, 0, st>>>(d);
+        note_launch("afb2d_direct_kernel");
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return set_last_cuda_error(e);
     }
@@ -1130,6 +1135,7 @@ static int run_sfb_chain(const float* yl, int64_t yl_ps, int64_t yl_rs, const fl
         d.Lh = Lh;
         d.t = p.t;
         sfb2d_direct_kernel<<<(unsigned)direct_grid((size_t)planes * d.lv.out_h * d.lv.out_w), kThreads, 0, st>>>(d);
+        note_launch("sfb2d_direct_kernel");
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return set_last_cuda_error(e);
     }

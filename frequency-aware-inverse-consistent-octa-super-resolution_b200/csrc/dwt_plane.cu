@@ -257,6 +257,7 @@ static int launch_afb_plane_t(const AfbParams& p, int first, cudaStream_t st) {
     }
     const size_t smem = afb_plane_floats(p, first) * sizeof(float);
     kernel<<<(unsigned)p.planes, kPlaneNT, smem, st>>>(p, first);
+    note_launch("afb_plane_kernel");
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? B200W_OK : set_last_cuda_error(e);
 }
@@ -481,6 +482,7 @@ static int launch_sfb_plane_t(const SfbParams& p, int count, cudaStream_t st) {
     const SfbPlanePlan pl = sfb_plane_plan(p, count);
     kernel<<<(unsigned)p.planes, kPlaneNT, pl.total() * sizeof(float), st>>>(p, count, (int)pl.out_sz, (int)pl.low_sz,
                                                                              (int)pl.hi_sz);
+    note_launch("sfb_plane_kernel");
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? B200W_OK : set_last_cuda_error(e);
 }

@@ -641,6 +641,7 @@ static int launch_afb_stream_t(AfbParams& p, int sms, cudaStream_t st) {
     }
 #endif
     afb_stream_kernel<L, S><<<(unsigned)base, kStreamNT, C::smem, st>>>(p);
+    note_launch("afb_stream_kernel");
     const cudaError_t e = cudaGetLastError();
 #ifdef B200W_TIMELINE
     if (tl_path && base <= 65536) {
@@ -687,7 +688,12 @@ static bool afb_owner_plan_t(const AfbParams& p, int sms, int j0_min, bool force
     int parts = std::min(kMaxParts, std::max(1, sms / p.planes));
     if (wraps) parts = 1;   // a part would need rows from the far end of the image
     parts = std::min(parts, p.lv[J - 1].Ho);
-    if (!force && (long long)p.planes * parts < sms / 2) return false;   // too few CTAs: the chain kernels spread better
+    if (!force) {
+        // one CTA per SM: too few CTAs leave the device idle (the chain kernels spread better), and a short last
+        // wave wastes up to half of the time
+        const long long ctas = (long long)p.planes * parts, waves = (ctas + sms - 1) / sms;
+        if (ctas < sms / 2 || ctas * 4 < waves * sms * 3) return false;
+    }
     op.p = p;
     op.parts = parts;
     op.ring_floats = (int)((size_t)(NT / 32) * C::D * C::STAGE * 4);
@@ -790,6 +796,7 @@ static int launch_afb_owner_t(const AfbOwnerParams& op, cudaStream_t st) {
     }
 #endif
     afb_owner_kernel<L, S><<<(unsigned)(op.p.planes * op.parts), NT, floats * 4, st>>>(op);
+    note_launch("afb_owner_kernel");
     const cudaError_t e = cudaGetLastError();
 #ifdef B200W_TIMELINE
     if (tl_path && ncta <= 65536) {

@@ -536,7 +536,12 @@ static bool sfb_owner_plan_t(const SfbParams& p, int sms, bool force, SfbOwnerPa
     int parts = std::min(kMaxParts, std::max(1, sms / p.planes));
     if (PER) parts = 1;   // the coefficient rows wrap around: a part would need rows from the far end
     parts = std::min(parts, p.lv[J - 1].out_h);
-    if (!force && (long long)p.planes * parts < sms / 2) return false;
+    if (!force) {
+        // one CTA per SM: too few CTAs leave the device idle (the chain kernels spread better), and a short last
+        // wave wastes up to half of the time
+        const long long ctas = (long long)p.planes * parts, waves = (ctas + sms - 1) / sms;
+        if (ctas < sms / 2 || ctas * 4 < waves * sms * 3) return false;
+    }
     op.p = p;
     op.parts = parts;
     // ring of the staging variants this launch can use (64-bit copies with the mode's shift, or 32-bit copies)
@@ -623,6 +628,7 @@ static int launch_sfb_owner_t(const SfbOwnerParams& op, cudaStream_t st) {
     }
     const size_t smem = ((size_t)op.ring_floats + op.y_floats) * 4;
     sfb_owner_kernel<L, S2V><<<(unsigned)(op.p.planes * op.parts), NT, smem, st>>>(op);
+    note_launch("sfb_owner_kernel");
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? B200W_OK : set_last_cuda_error(e);
 }
@@ -693,6 +699,7 @@ static int launch_sfb_stream_t(SfbParams& p, int sms, cudaStream_t st) {
         if (rc) return rc;
     }
     sfb_stream_kernel<L, S2V><<<(unsigned)base, kStreamNT, SfbSmem<L>::value, st>>>(p);
+    note_launch("sfb_stream_kernel");
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? B200W_OK : set_last_cuda_error(e);
 }

@@ -73,6 +73,7 @@ extern "C" int b200w_freq_mask_c64(void* spec, int planes, int rows, int cols, f
     const size_t total = (size_t)planes * rows * wh;
     freq_mask_kernel<<<pointwise_grid(total), 256, 0, (cudaStream_t)stream>>>((float2*)spec, planes, rows, cols, wh,
                                                                               0.5f / (radius * radius), highpass ? 1 : 0);
+    b200w::note_launch("freq_mask_kernel");
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? B200W_OK : set_last_cuda_error(e);
 }
@@ -84,6 +85,7 @@ extern "C" int b200w_abs_sign_f32(const float* x, float* y, size_t n, float sign
     const size_t n4 = vec ? n / 4 : 0;
     abs_sign_kernel<<<pointwise_grid(n4 ? n4 : n), 256, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)y, n4, x, y, n,
                                                                                   sign);
+    b200w::note_launch("abs_sign_kernel");
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? B200W_OK : set_last_cuda_error(e);
 }
@@ -92,6 +94,7 @@ extern "C" int b200w_sign_mul_f32(const float* g, const float* x, float* out, si
     if (!g || !x || !out) return B200W_ERR_NULL_POINTER;
     if (n == 0) return B200W_OK;
     sign_mul_kernel<<<pointwise_grid(n), 256, 0, (cudaStream_t)stream>>>(g, x, out, n, sign);
+    b200w::note_launch("sign_mul_kernel");
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? B200W_OK : set_last_cuda_error(e);
 }

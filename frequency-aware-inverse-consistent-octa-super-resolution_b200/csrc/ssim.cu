@@ -305,6 +305,7 @@ static int launch_ssim(const SsimParams& p, cudaStream_t st) {
     if (e != cudaSuccess) return set_last_cuda_error(e);
     const size_t grid = (size_t)p.planes * p.nseg * p.strips;
     kern<<<(unsigned)grid, kThreads, smem, st>>>(p);
+    note_launch(FWD ? "ssim_stream_kernel<fwd>" : "ssim_stream_kernel<bwd>");
     e = cudaGetLastError();
     return e == cudaSuccess ? B200W_OK : set_last_cuda_error(e);
 }
@@ -364,6 +365,7 @@ extern "C" int b200w_ssim_fwd_f32(const float* img1, const float* img2, int N, i
     const int per_out = size_average ? p.planes * per_plane : C * per_plane;
     const double inv = size_average ? 1.0 / ((double)N * C * H * W) : 1.0 / ((double)C * H * W);
     ssim_finalize_kernel<<<nout, kThreads, 0, st>>>(p.partials, per_out, inv, out);
+    note_launch("ssim_finalize_kernel");
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? B200W_OK : set_last_cuda_error(e);
 }

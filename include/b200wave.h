@@ -85,6 +85,10 @@ int b200w_abi_version(void);
 const char* b200w_status_string(int status);
 /* last cudaError_t seen by a failing launch on this thread (0 = none); for diagnostics only */
 int b200w_last_cuda_error(void);
+/* diagnostics: number of kernels this library has launched in the process, and the name of the `back`-th most
+ * recent one ("" when out of range; the last 64 are kept).  bench.py counts its `gpu_launches` with these. */
+unsigned long long b200w_kernel_launches(void);
+const char* b200w_kernel_log(int back);
 
 /* floor((n+l-1)/2), or ceil(n/2) for periodization; negative status for a bad mode */
 int b200w_dwt_coeff_len(int n, int l, int mode);

@@ -17,7 +17,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_launch.log 2>&1
 # ncu: full captures of the hot kernels
 python tools/prof_dwt.py 64 304 db3 symmetric 3 > $O/plain_a.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:stream_kernel -s 2 -c 2 -f -o $O/prof_cfg2_chain \
+ncu --set full --clock-control none --import-source on -k "regex:stream_kernel|owner_kernel" -s 2 -c 2 -f -o $O/prof_cfg2_chain \
     python tools/prof_dwt.py 64 304 db3 symmetric 3 > $O/ncu_a.log 2>&1
 python tools/prof_dwt.py 64 304 db3 symmetric 1 > $O/plain_b.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:stream_kernel -s 2 -c 2 -f -o $O/prof_cfg2_level1 \
