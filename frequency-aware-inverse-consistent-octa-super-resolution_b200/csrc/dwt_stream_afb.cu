@@ -177,6 +177,7 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
     const int slot = lane + (NV - 1) * (seg - seg_first);
     const bool run_last = NV > 1 && active && (lane == 31 || cpl == ncpA - 1);
     const long long rs = lv.x_rs;
+    const unsigned rs_b = (unsigned)rs * 4u;                      // row stride in bytes (< 4 GB, checked by the host)
     const float* xcol = lv.x + (long long)plane * lv.x_ps + cb;   // column cb of row 0
     float4* ring = ring_all + (size_t)(tid >> 5) * D * C::STAGE;
     const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring) + (unsigned)slot * 16u;
@@ -193,7 +194,8 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
                 const int sr = OWNER ? own.rmap[2 * (i0 - own.c0) + 2 * q + e] : afb_src_row(r0 + 2 * q + e, H, Hreal, mode);
                 const unsigned dst = ring_s + (unsigned)((st * 2 + e) * C::RP) * 16u;
                 if (sr >= 0) {
-                    const float* src = xcol + (long long)sr * rs;
+                    const float* src = reinterpret_cast<const float*>(reinterpret_cast<const char*>(xcol) +
+                                                                      (unsigned long long)(unsigned)sr * rs_b);
                     cp_async<4>(dst, src);
                     if (run_last) {
 #pragma unroll
@@ -213,8 +215,12 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
 
     const int Wo = lv.Wo;
     const size_t band = (size_t)lv.Ho * Wo;
-    const bool v2lo = lv.low_vec2 != 0, v2hi = lv.out_vec2 != 0;
-    const bool st_low = lv.st_low != 0, st_hi = lv.st_hi != 0;
+    // store switches of the level in one register (kept there: re-reading them from the parameter block inside the
+    // loop costs an indexed constant load each)
+    unsigned flags = (lv.low_vec2 ? 1u : 0u) | (lv.out_vec2 ? 2u : 0u) | (lv.st_low ? 4u : 0u) | (lv.st_hi ? 8u : 0u) |
+                     ((lv.hi_scale != 1.f || lv.hi_shift != 0.f) ? 16u : 0u);
+    asm volatile("" : "+r"(flags));
+    const bool v2lo = flags & 1u, v2hi = flags & 2u, st_low = flags & 4u, st_hi = flags & 8u;
     const float2 hsc = make_float2(lv.hi_scale, lv.hi_scale), hsh = make_float2(lv.hi_shift, lv.hi_shift);
     const long long low_rs = lv.low_rs;
     float* q0 = lv.low + (long long)plane * lv.low_ps + (long long)i0 * low_rs + 2 * cp;   // only dereferenced if st_low
@@ -578,6 +584,7 @@ bool afb_stream_supported(const AfbParams& p, int L) {
     for (int j = 0; j < p.J; ++j) {
         const AfbLevel& lv = p.lv[j];
         if ((lv.x_rs & 3) || (lv.x_ps & 3) || !aligned_to(lv.x, 16)) return false;
+        if (lv.x_rs < 0 || lv.x_rs >= (1LL << 30)) return false;   // the ring addresses rows with a 32-bit byte stride
         if (lv.offW != afb_off(L, per) || lv.offH != afb_off(L, per)) return false;
     }
     return true;

@@ -22,6 +22,7 @@
 // the natural size crop.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include "dwt_levels.cuh"
 
 namespace b200w {
@@ -413,6 +414,16 @@ __global__ void __launch_bounds__(kStreamNT, SfbStreamCfg<L, S2V>::MINB) sfb_str
     }
 }
 
+#ifdef B200W_TIMELINE
+// debug build only: per-CTA timestamps of the last owner launch (tools/timeline_owner.py)
+__device__ unsigned long long* g_sfb_timeline = nullptr;
+__device__ __forceinline__ unsigned long long sfb_gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
 // ---- owner kernel: every position of a synthesis chain for one (plane, part) in one CTA ------------------------
 // The coarsest position reads its low-pass input from global memory through the ring like the stream kernel; every
 // output but the last stays in shared memory, where the next position reads it as its low-pass input (SMEM_LOW),
@@ -431,6 +442,16 @@ __global__ void __launch_bounds__(SfbOwnerCfg<L>::NT, 1) sfb_owner_kernel(const 
     const int plane = blockIdx.x / op.parts;
     const int part = blockIdx.x - plane * op.parts;
     float* const y_area = reinterpret_cast<float*>(sfb_ring_all) + op.ring_floats;
+#ifdef B200W_TIMELINE
+    // slot 0 / 14: %globaltimer at start / end; slot 15: clock at start; slots 1 + 3*c + {0,1,2}: clock after the
+    // set-up, the interior passes and the border passes of chain position c
+#define SFB_OWN_MARK(slot, v) do { if (g_sfb_timeline && tid == 0) g_sfb_timeline[(size_t)blockIdx.x * 16 + (slot)] = (v); } while (0)
+    SFB_OWN_MARK(0, sfb_gtime());
+    SFB_OWN_MARK(15, (unsigned long long)clock64());
+    SFB_OWN_MARK(13, (unsigned long long)clock64());
+#else
+#define SFB_OWN_MARK(slot, v) do { } while (0)
+#endif
 #pragma unroll 1
     for (int c = 0; c < p.J; ++c) {
         SfbLevel lv = p.lv[c];
@@ -458,6 +479,7 @@ __global__ void __launch_bounds__(SfbOwnerCfg<L>::NT, 1) sfb_owner_kernel(const 
         lv.Rp = ol.R;
         const int npairs = ((lv.offH + own.n1 - 1) >> 1) + 1 - ((own.n0 + lv.offH) >> 1);
         own.itemsA = ((npairs + lv.Rp - 1) / lv.Rp) * lv.ntA;
+        SFB_OWN_MARK(1 + 3 * c, (unsigned long long)clock64());
         for (int base = 0; base < own.itemsA; base += NT) {
             __syncwarp();   // the warp's ring is reused from pass to pass
             const int it = base + tid;
@@ -469,12 +491,18 @@ __global__ void __launch_bounds__(SfbOwnerCfg<L>::NT, 1) sfb_owner_kernel(const 
                 else sfb_ring_cta<L, 1, 0, true, false>(p, lv, plane, it, sfb_ring_all, nullptr, 0u, own);
             }
         }
+#ifdef B200W_TIMELINE
+        __syncthreads();
+        SFB_OWN_MARK(2 + 3 * c, (unsigned long long)clock64());
+#endif
         // border columns go to the last threads first: warps with no or short segments start them early
         const int itemsB = (own.n1 - own.n0) * (lv.nA0 + lv.out_w - lv.nA1);
         for (int it = NT - 1 - tid; it < itemsB; it += NT)
             sfb_border_item<L, true>(p, lv, plane, it, true, nullptr, 0u, own);
         __syncthreads();   // this position's output is complete before the next one reads it
+        SFB_OWN_MARK(3 + 3 * c, (unsigned long long)clock64());
     }
+    SFB_OWN_MARK(14, sfb_gtime());
 }
 
 static int sfb_env_int(const char* name, int dflt) {
@@ -627,9 +655,28 @@ static int launch_sfb_owner_t(const SfbOwnerParams& op, cudaStream_t st) {
         attr_set = true;
     }
     const size_t smem = ((size_t)op.ring_floats + op.y_floats) * 4;
+#ifdef B200W_TIMELINE
+    static unsigned long long* tl = nullptr;
+    const char* tl_path = getenv("B200W_TIMELINE_FILE_SFB");
+    const size_t ncta = (size_t)op.p.planes * op.parts;
+    if (tl_path && ncta <= 65536) {
+        if (!tl) cudaMalloc(&tl, sizeof(unsigned long long) * 16 * 65536);
+        cudaMemsetAsync(tl, 0, sizeof(unsigned long long) * 16 * 65536, st);
+        cudaMemcpyToSymbolAsync(g_sfb_timeline, &tl, sizeof(tl), 0, cudaMemcpyHostToDevice, st);
+    }
+#endif
     sfb_owner_kernel<L, S2V><<<(unsigned)(op.p.planes * op.parts), NT, smem, st>>>(op);
     note_launch("sfb_owner_kernel");
     const cudaError_t e = cudaGetLastError();
+#ifdef B200W_TIMELINE
+    if (tl_path && ncta <= 65536) {
+        cudaStreamSynchronize(st);
+        static unsigned long long host[16 * 65536];
+        cudaMemcpy(host, tl, sizeof(unsigned long long) * 16 * ncta, cudaMemcpyDeviceToHost);
+        FILE* f = fopen(tl_path, "wb");
+        if (f) { fwrite(host, sizeof(unsigned long long) * 16, ncta, f); fclose(f); }
+    }
+#endif
     return e == cudaSuccess ? B200W_OK : set_last_cuda_error(e);
 }
 

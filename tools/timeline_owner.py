@@ -7,6 +7,7 @@ import sys
 import numpy as np
 
 a = np.fromfile(sys.argv[1], dtype=np.uint64).reshape(-1, 16)
+a = a[1:]            # row 0 also receives the stream-kernel marks of every CTA (item index 0)
 a = a[a[:, 0] > 0]
 GHZ = 1.965
 t0 = a[:, 0].min()
@@ -17,7 +18,7 @@ ck = lambda k: (a[:, k].astype(np.int64) - a[:, 15].astype(np.int64)) / (GHZ * 1
 prev = ck(13)
 print('maps (all levels) %.2f us' % np.median(prev))
 for j in range(4):
-    if not (a[:, 1 + 3 * j] > 0).any():
+    if 3 + 3 * j > 12 or not (np.median(a[:, 1 + 3 * j]) > 0):
         break
     m, i, b = ck(1 + 3 * j), ck(2 + 3 * j), ck(3 + 3 * j)
     print("level +%d: maps %.2f us | interior %.2f (max %.2f) | border %.2f (max %.2f) | level end at %.2f (max %.2f)" % (
