@@ -71,6 +71,9 @@ struct AfbParams {
 // the CTA's shared memory, so the dependent levels cost a block barrier instead of a trip through L2 and a
 // grid-wide dependency.  Parts of a plane overlap by the few rows the deeper levels need (recomputed, not shared).
 constexpr int kMaxParts = 4;
+#ifndef B200W_OWNER_NT
+#define B200W_OWNER_NT 384   // threads of an owner CTA for filters up to 8 taps: 12 warps with up to 168 registers each (measured best of 256..512, profiles/r01_notes.md)
+#endif
 struct OwnerLevel {
     int R;                 // output rows per thread segment
     int pitch;             // row pitch (floats, multiple of 4) of this level's low-pass image in shared memory

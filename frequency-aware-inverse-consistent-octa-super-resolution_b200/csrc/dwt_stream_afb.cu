@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(kStreamNT, AfbStreamCfg<L, S>::MINB) afb_strea
 template <int L>
 struct AfbOwnerCfg {
     // one CTA per SM; long filters need more than 128 registers per thread
-    static constexpr int NT = L <= 8 ? 512 : 256;
+    static constexpr int NT = L <= 8 ? B200W_OWNER_NT : 256;
 };
 
 template <int L, int S>
@@ -766,8 +766,11 @@ static bool afb_owner_plan_t(const AfbParams& p, int sms, int j0_min, bool force
             if ((NT - spare) / ncpA < 1) spare = 0;
             const int rmax = std::max(16, 4 * (H2 - 1));
             int R = std::max(rmin, ceil_div(rows, std::max(1, (NT - spare) / ncpA)));
-            if (R > rmax) R = std::max(rmin, ceil_div(rows, std::max(1, NT / ncpA)));   // no room: one class after the other
-            R = std::min(R, rmax);
+            if (R > rmax) {   // no room for spare warps: one class after the other
+                R = std::max(rmin, ceil_div(rows, std::max(1, NT / ncpA)));
+                // one pass of somewhat longer segments beats a second, mostly empty pass; far longer ones do not
+                if (R > 2 * rmax) R = rmax;
+            }
             if (stream_rows_override() > 0) R = stream_rows_override();
             op.ol[j].R = std::max(1, std::min(R, rows));
         }

@@ -430,7 +430,7 @@ __device__ __forceinline__ unsigned long long sfb_gtime() {
 // the detail bands still streaming in through the ring.  One block barrier per position, no tickets or counters.
 template <int L>
 struct SfbOwnerCfg {
-    static constexpr int NT = L <= 8 ? 512 : 256;   // one CTA per SM; long filters need > 128 registers per thread
+    static constexpr int NT = L <= 8 ? B200W_OWNER_NT : 256;   // one CTA per SM; long filters need > 128 registers per thread
 };
 
 template <int L, int S2V>
@@ -635,7 +635,8 @@ static bool sfb_owner_plan_t(const SfbParams& p, int sms, bool force, SfbOwnerPa
         const int npairs = ((lv.offH + rows - 1) >> 1) + 2;   // upper bound over the parts' row offsets
         const int ntA = std::max(1, lv.ntA);
         int Rp = std::max(std::max(2, H2 - 1), ceil_div(npairs, std::max(1, NT / ntA)));
-        Rp = std::min(Rp, std::max(16, 4 * (H2 - 1)));
+        // one pass of somewhat longer segments beats a second, mostly empty pass; far longer ones do not
+        if (Rp > 2 * std::max(16, 4 * (H2 - 1))) Rp = std::max(16, 4 * (H2 - 1));
         if (stream_pairs_override() > 0) Rp = stream_pairs_override();
         ol.R = std::max(1, Rp);
     }
