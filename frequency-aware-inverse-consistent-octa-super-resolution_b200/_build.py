@@ -28,7 +28,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3",
     "-cudart", "static",
 ] + (["-DB200W_TIMELINE"] if os.environ.get("B200W_TIMELINE") == "1" else []) \
-  + (["-DB200W_OWNER_NT=%d" % int(os.environ["B200W_OWNER_NT"])] if os.environ.get("B200W_OWNER_NT") else [])
+  + (["-DB200W_OWNER_NT=%d" % int(os.environ["B200W_OWNER_NT"])] if os.environ.get("B200W_OWNER_NT") else []) \
+  + (["-DB200W_OWNER_Q=%d" % int(os.environ["B200W_OWNER_Q"])] if os.environ.get("B200W_OWNER_Q") else [])
 
 
 def find_nvcc():

@@ -71,6 +71,10 @@ struct AfbParams {
 // the CTA's shared memory, so the dependent levels cost a block barrier instead of a trip through L2 and a
 // grid-wide dependency.  Parts of a plane overlap by the few rows the deeper levels need (recomputed, not shared).
 constexpr int kMaxParts = 4;
+#ifndef B200W_OWNER_Q
+#define B200W_OWNER_Q 1      // column pairs per lane of the analysis owner kernel for filters up to 6 taps (2 was measured: 9 % fewer
+                             // instructions per pixel, but shorter segments with a larger warm-up share: 24.6 vs 20.1 us at cfg2)
+#endif
 #ifndef B200W_OWNER_NT
 #define B200W_OWNER_NT 384   // threads of an owner CTA for filters up to 8 taps: 12 warps with up to 168 registers each (measured best of 256..512, profiles/r01_notes.md)
 #endif

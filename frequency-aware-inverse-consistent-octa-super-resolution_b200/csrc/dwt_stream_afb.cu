@@ -47,6 +47,12 @@ struct AfbStreamCfg {
     // resident CTAs per SM the ring path is compiled for (caps the registers; the rare border path may spill)
     static constexpr int MINB = L <= 8 ? 5 : (L <= 12 ? 4 : 3);
     static constexpr size_t smem = sizeof(float4) * (size_t)(kStreamNT / 32) * D * STAGE;
+    // Q adjacent column pairs per lane (owner kernel, short filters: Q = 2 amortises the per-row-pair overhead --
+    // staging, addresses, loop control -- over twice the arithmetic): a lane stages Q float4 per input row
+    // (a warp of Q = 2 lanes may straddle up to 9 rows of >= 4 lanes each)
+    __host__ __device__ static constexpr int rp(int Q) { return 32 * Q + (Q == 1 ? kMaxRuns : 9) * (NV - 1); }
+    __host__ __device__ static constexpr int depth(int Q) { return Q == 1 ? D : 4; }
+    __host__ __device__ static constexpr int ring_float4_per_warp(int Q) { return depth(Q) * 2 * rp(Q); }
 };
 
 // source row of input row r: r itself inside the image, else the padding mode's map; -1 = zero row
@@ -151,21 +157,25 @@ __device__ __forceinline__ float4 lds128(unsigned addr) {
 // `it` = the thread's item (segment-major: segment * ncpA + interior column pair).  OWNER: the rows come from `own`
 // instead of the whole level; SMEM_SRC (owner kernel, dependent levels): the input image already lies in shared
 // memory, so a lane reads its window straight from there and the ring is not used.
-template <int L, int S, bool OWNER = false, bool SMEM_SRC = false>
+template <int L, int S, bool OWNER = false, bool SMEM_SRC = false, int Q = 1>
 __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel& lv, int plane, int it, float4* ring_all,
                                              const unsigned* wait_ctr, unsigned wait_need, unsigned item,
                                              const OwnRows& own) {
     using C = AfbStreamCfg<L, S>;
-    constexpr int H2 = C::H2, NV = C::NV, NE = C::NE, D = C::D;
+    constexpr int H2 = C::H2, NV = C::NV, NE = C::NE, D = C::depth(Q);
+    constexpr int RP = C::rp(Q), STAGE = 2 * RP;
+    constexpr int NVQ = NV + (Q - 1), NEQ = 4 * NVQ;   // float4 / floats of a lane's window (Q pairs)
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int itemsA = OWNER ? own.itemsA : lv.itemsA;
     const bool active = it < itemsA;
     const int ncpA = lv.ncpA;
+    const int nq = Q == 1 ? ncpA : (ncpA + Q - 1) / Q;   // lanes per row
     const int itc = active ? it : itemsA - 1;        // inactive lanes shadow the last item (no copies, no stores)
-    const int seg = itc / ncpA;
-    const int cpl = itc - seg * ncpA;
-    const int cp = lv.cp0A + cpl;
+    const int seg = itc / nq;
+    const int cpl = itc - seg * nq;
+    const int cp = lv.cp0A + Q * cpl;
+    const bool second = Q == 2 && Q * cpl + 1 < ncpA;   // the lane's second column pair exists (odd pair counts)
     const int i0 = (OWNER ? own.c0 : 0) + seg * lv.R;   // first output row of the segment
     const int nout = min(lv.R, (OWNER ? own.c1 : lv.Ho) - i0);
     const int npairs = active ? nout + H2 - 1 : 0;   // input row pairs feeding them
@@ -174,12 +184,16 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
     const int cb = 4 * cp - (lv.offW + S);           // first column of the window: >= 0, multiple of 4
     // position in the ring row: own float4 at slot lane + (NV-1)*run; the last lane of a run adds the NV-1 extras
     const int seg_first = __shfl_sync(0xffffffffu, seg, 0);
-    const int slot = lane + (NV - 1) * (seg - seg_first);
-    const bool run_last = NV > 1 && active && (lane == 31 || cpl == ncpA - 1);
+    const int slot = Q * lane + (NV - 1) * (seg - seg_first);
+    const bool run_last = NV > 1 && active && (lane == 31 || cpl == nq - 1);
+    // float4 the lane copies per row: its own Q (a missing second pair's float4 still belongs to the first pair's
+    // window when NV > 1) and, at the end of a run, the rest of the last window
+    const int ncopy = (Q == 2 && (second || NV > 1) ? 2 : 1);
+    const int nextra = run_last ? (NV - 1) - (Q == 2 && !second ? 1 : 0) : 0;
     const long long rs = lv.x_rs;
     const unsigned rs_b = (unsigned)rs * 4u;                      // row stride in bytes (< 4 GB, checked by the host)
     const float* xcol = lv.x + (long long)plane * lv.x_ps + cb;   // column cb of row 0
-    float4* ring = ring_all + (size_t)(tid >> 5) * D * C::STAGE;
+    float4* ring = ring_all + (size_t)(tid >> 5) * D * STAGE;
     const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring) + (unsigned)slot * 16u;
 
     // stage one input row pair (pair index q of this lane's segment) into ring stage `st`.  Rows inside the image
@@ -192,21 +206,25 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int sr = OWNER ? own.rmap[2 * (i0 - own.c0) + 2 * q + e] : afb_src_row(r0 + 2 * q + e, H, Hreal, mode);
-                const unsigned dst = ring_s + (unsigned)((st * 2 + e) * C::RP) * 16u;
+                const unsigned dst = ring_s + (unsigned)((st * 2 + e) * RP) * 16u;
                 if (sr >= 0) {
                     const float* src = reinterpret_cast<const float*>(reinterpret_cast<const char*>(xcol) +
                                                                       (unsigned long long)(unsigned)sr * rs_b);
                     cp_async<4>(dst, src);
+                    if (Q == 2 && ncopy == 2) cp_async<4>(dst + 16u, src + 4);
                     if (run_last) {
 #pragma unroll
-                        for (int k = 1; k < NV; ++k) cp_async<4>(dst + 16u * k, src + 4 * k);
+                        for (int k = 0; k < NV - 1; ++k)
+                            if (k < nextra) cp_async<4>(dst + 16u * (ncopy + k), src + 4 * (ncopy + k));
                     }
                 } else {
-                    float4* d = ring + (st * 2 + e) * C::RP + slot;
+                    float4* d = ring + (st * 2 + e) * RP + slot;
                     d[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (Q == 2 && ncopy == 2) d[1] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (run_last) {
 #pragma unroll
-                        for (int k = 1; k < NV; ++k) d[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int k = 0; k < NV - 1; ++k)
+                            if (k < nextra) d[ncopy + k] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
             }
@@ -244,7 +262,7 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
     // SMEM_SRC: shared address of this lane's window in source row 0
     const unsigned win_s = SMEM_SRC ? own.src_s + (unsigned)(cb - own.src_row0 * (int)rs) * 4u : 0u;
     int orow = i0;         // OWNER: output row the next store belongs to
-    float2 acc[H2][4];   // ring of pending output rows: LL, LH, HL, HH, each (column 0, column 1)
+    float2 acc[Q][H2][4];   // per pair: ring of pending output rows: LL, LH, HL, HH, each (column 0, column 1)
     int st_r = 0, st_w = D - 1;
     constexpr bool kRotate = L >= 10;
     constexpr int UQ = kRotate ? 1 : H2;
@@ -262,49 +280,68 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
                     st_w = st_w + 1 == D ? 0 : st_w + 1;
                 }
                 {
-                    float v[2][NE];
+                    float v[2][NEQ];
+                    // a lane without a second pair reads one float4 less (it was not staged / may lie past the row)
+                    const int nv = NVQ - (Q == 2 && !second ? 1 : 0);
                     if (SMEM_SRC) {
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             const int sr = q < npairs ? own.rmap[2 * (i0 - own.c0) + 2 * q + e] : -1;
                             const unsigned a = win_s + (unsigned)(max(sr, 0) * (int)rs) * 4u;
 #pragma unroll
-                            for (int k = 0; k < NV; ++k) {
+                            for (int k = 0; k < NVQ; ++k) {
                                 float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (sr >= 0) t = lds128(a + 16u * k);
+                                if (sr >= 0 && k < nv) t = lds128(a + 16u * k);
                                 v[e][4 * k] = t.x; v[e][4 * k + 1] = t.y; v[e][4 * k + 2] = t.z; v[e][4 * k + 3] = t.w;
                             }
                         }
                     } else {
-                        const float4* src = ring + (st_r * 2) * C::RP + slot;
+                        const float4* src = ring + (st_r * 2) * RP + slot;
 #pragma unroll
                         for (int e = 0; e < 2; ++e)
 #pragma unroll
-                            for (int k = 0; k < NV; ++k) {
-                                const float4 t = src[e * C::RP + k];
+                            for (int k = 0; k < NVQ; ++k) {
+                                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (Q == 1 || k < nv) t = src[e * RP + k];
                                 v[e][4 * k] = t.x; v[e][4 * k + 1] = t.y; v[e][4 * k + 2] = t.z; v[e][4 * k + 3] = t.w;
                             }
                     }
-                    afb_pair_fma<L, S, NE>(p.t, v, acc, ph);
+#pragma unroll
+                    for (int u = 0; u < Q; ++u) {
+                        float vu[2][NE];   // the pair's window: a register renaming, not a copy
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+#pragma unroll
+                            for (int k = 0; k < NE; ++k) vu[e][k] = v[e][4 * u + k];
+                        afb_pair_fma<L, S, NE>(p.t, vu, acc[u], ph);
+                    }
                     // output row q - (H2-1) has now seen all its L input rows
                     if (q >= H2 - 1 && q < npairs) {
-                        const float2* s = acc[kRotate ? 0 : (ph + 1) % H2];
-                        if (st_low) {
-                            if (v2lo) {
-                                *reinterpret_cast<float2*>(q0) = s[0];
-                            } else {
-                                q0[0] = s[0].x; q0[1] = s[0].y;
-                            }
-                        }
-                        if (st_hi && (!OWNER || (orow >= own.h0 && orow < own.h1))) {
-                            const float2 lh = ffma2(s[1], hsc, hsh), hl = ffma2(s[2], hsc, hsh), hh = ffma2(s[3], hsc, hsh);
-                            if (v2hi) {
-                                *reinterpret_cast<float2*>(q1) = lh;
-                                *reinterpret_cast<float2*>(q1 + band) = hl;
-                                *reinterpret_cast<float2*>(q1 + 2 * band) = hh;
-                            } else {
-                                q1[0] = lh.x; q1[band] = hl.x; q1[2 * band] = hh.x;
-                                q1[1] = lh.y; q1[band + 1] = hl.y; q1[2 * band + 1] = hh.y;
+                        const bool hi_row = st_hi && (!OWNER || (orow >= own.h0 && orow < own.h1));
+#pragma unroll
+                        for (int u = 0; u < Q; ++u) {
+                            if (u == 0 || second) {
+                                const float2* s = acc[u][kRotate ? 0 : (ph + 1) % H2];
+                                float* d0 = q0 + 2 * u;
+                                float* d1 = q1 + 2 * u;
+                                if (st_low) {
+                                    if (v2lo) {
+                                        *reinterpret_cast<float2*>(d0) = s[0];
+                                    } else {
+                                        d0[0] = s[0].x; d0[1] = s[0].y;
+                                    }
+                                }
+                                if (hi_row) {
+                                    const float2 lh = ffma2(s[1], hsc, hsh), hl = ffma2(s[2], hsc, hsh), hh = ffma2(s[3], hsc, hsh);
+                                    if (v2hi) {
+                                        *reinterpret_cast<float2*>(d1) = lh;
+                                        *reinterpret_cast<float2*>(d1 + band) = hl;
+                                        *reinterpret_cast<float2*>(d1 + 2 * band) = hh;
+                                    } else {
+                                        d1[0] = lh.x; d1[band] = hl.x; d1[2 * band] = hh.x;
+                                        d1[1] = lh.y; d1[band + 1] = hl.y; d1[2 * band + 1] = hh.y;
+                                    }
+                                }
                             }
                         }
                         q0 += low_rs;
@@ -313,9 +350,11 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
                     }
                     if (kRotate) {
 #pragma unroll
-                        for (int k = 0; k + 1 < H2; ++k)
+                        for (int u = 0; u < Q; ++u)
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) acc[k][i] = acc[k + 1][i];
+                            for (int k = 0; k + 1 < H2; ++k)
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) acc[u][k][i] = acc[u][k + 1][i];
                     }
                 }
                 st_r = st_r + 1 == D ? 0 : st_r + 1;
@@ -460,12 +499,14 @@ template <int L>
 struct AfbOwnerCfg {
     // one CTA per SM; long filters need more than 128 registers per thread
     static constexpr int NT = L <= 8 ? B200W_OWNER_NT : 256;
+    // column pairs per lane: two for the short filters (their accumulators fit the register budget twice)
+    static constexpr int Q = L <= 6 ? B200W_OWNER_Q : 1;
 };
 
 template <int L, int S>
 __global__ void __launch_bounds__(AfbOwnerCfg<L>::NT, 1) afb_owner_kernel(const __grid_constant__ AfbOwnerParams op) {
     extern __shared__ float4 ring_all[];
-    constexpr int NT = AfbOwnerCfg<L>::NT;
+    constexpr int NT = AfbOwnerCfg<L>::NT, Q = AfbOwnerCfg<L>::Q;
     const AfbParams& p = op.p;
     const int tid = threadIdx.x;
     const int plane = blockIdx.x / op.parts;
@@ -530,7 +571,7 @@ __global__ void __launch_bounds__(AfbOwnerCfg<L>::NT, 1) afb_owner_kernel(const 
         }
         lv.R = ol.R;
         const int nrows = own.c1 - own.c0;
-        own.itemsA = ((nrows + lv.R - 1) / lv.R) * lv.ncpA;
+        own.itemsA = ((nrows + lv.R - 1) / lv.R) * ((lv.ncpA + Q - 1) / Q);
         own.rmap = maps + ol.map_off;
         own.cmap = own.rmap + 2 * nrows + L;
         OWN_MARK(1 + 3 * (j - op.j0), (unsigned long long)clock64());
@@ -545,9 +586,9 @@ __global__ void __launch_bounds__(AfbOwnerCfg<L>::NT, 1) afb_owner_kernel(const 
             for (int base = 0; base < own.itemsA; base += ntA) {
                 __syncwarp();   // the warp's ring is reused from pass to pass
                 if (smem_src)
-                    afb_ring_cta<L, S, true, true>(p, lv, plane, base + tid, ring_all, nullptr, 0u, 0u, own);
+                    afb_ring_cta<L, S, true, true, Q>(p, lv, plane, base + tid, ring_all, nullptr, 0u, 0u, own);
                 else
-                    afb_ring_cta<L, S, true, false>(p, lv, plane, base + tid, ring_all, nullptr, 0u, 0u, own);
+                    afb_ring_cta<L, S, true, false, Q>(p, lv, plane, base + tid, ring_all, nullptr, 0u, 0u, own);
             }
         }
 #ifdef B200W_TIMELINE
@@ -687,7 +728,7 @@ constexpr size_t kOwnerSmemMax = 227 * 1024;
 template <int L, int S>
 static bool afb_owner_plan_t(const AfbParams& p, int sms, int j0_min, bool force, AfbOwnerParams& op) {
     using C = AfbStreamCfg<L, S>;
-    constexpr int NT = AfbOwnerCfg<L>::NT;
+    constexpr int NT = AfbOwnerCfg<L>::NT, Q = AfbOwnerCfg<L>::Q;
     constexpr int H2 = L / 2;
     const int J = p.J;
     if (J < 2 || j0_min > J - 2) return false;
@@ -703,7 +744,7 @@ static bool afb_owner_plan_t(const AfbParams& p, int sms, int j0_min, bool force
     }
     op.p = p;
     op.parts = parts;
-    op.ring_floats = (int)((size_t)(NT / 32) * C::D * C::STAGE * 4);
+    op.ring_floats = (int)((size_t)(NT / 32) * C::ring_float4_per_warp(Q) * 4);
     // rows: every level's output rows are split evenly over the parts (what a part stores); a part computes those
     // plus whatever the next level's computed rows read through the row extension
     for (int j = 0; j < J; ++j) {
@@ -757,7 +798,7 @@ static bool afb_owner_plan_t(const AfbParams& p, int sms, int j0_min, bool force
             // segments sized so that one pass of the CTA's threads covers the part
             int rows = 0;
             for (int q = 0; q < parts; ++q) rows = std::max(rows, op.ol[j].c1[q] - op.ol[j].c0[q]);
-            const int ncpA = std::max(1, op.p.lv[j].ncpA);
+            const int ncpA = std::max(1, (op.p.lv[j].ncpA + Q - 1) / Q);   // lanes per row
             const int rmin = std::max(2, H2 - 1);
             // some warps are kept free for the border positions (about four rounds of them), which then run
             // beside the interior segments instead of after them
