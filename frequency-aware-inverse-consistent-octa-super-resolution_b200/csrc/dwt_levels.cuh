@@ -70,7 +70,7 @@ struct AfbParams {
 // first of them streams its input rows from global memory, the low-pass image of every level but the last stays in
 // the CTA's shared memory, so the dependent levels cost a block barrier instead of a trip through L2 and a
 // grid-wide dependency.  Parts of a plane overlap by the few rows the deeper levels need (recomputed, not shared).
-constexpr int kMaxParts = 4;
+constexpr int kMaxParts = 8;
 #ifndef B200W_OWNER_Q
 #define B200W_OWNER_Q 1      // column pairs per lane of the analysis owner kernel for filters up to 6 taps (2 was measured: 9 % fewer
                              // instructions per pixel, but shorter segments with a larger warm-up share: 24.6 vs 20.1 us at cfg2)
@@ -93,6 +93,8 @@ struct AfbOwnerParams {
     int ring_floats;       // size of the staging rings that precede the maps and the low-pass area
     int map_ints;          // size of the extension-map area (all levels)
 };
+
+static_assert(sizeof(AfbOwnerParams) <= 4096, "kernel parameter block");
 
 // ---- synthesis -----------------------------------------------------------------------------------
 struct SfbLevel {

@@ -737,10 +737,10 @@ static bool afb_owner_plan_t(const AfbParams& p, int sms, int j0_min, bool force
     if (wraps) parts = 1;   // a part would need rows from the far end of the image
     parts = std::min(parts, p.lv[J - 1].Ho);
     if (!force) {
-        // one CTA per SM: too few CTAs leave the device idle (the chain kernels spread better), and a short last
-        // wave wastes up to half of the time
+        // one CTA per SM: a short last wave wastes up to half of the time (few CTAs are fine: small batches are
+        // latency-bound either way, and measured faster here than as ticketed chains, profiles/r01_smallbatch.log)
         const long long ctas = (long long)p.planes * parts, waves = (ctas + sms - 1) / sms;
-        if (ctas < sms / 2 || ctas * 4 < waves * sms * 3) return false;
+        if (ctas * 4 < waves * sms * 3 && waves > 1) return false;
     }
     op.p = p;
     op.parts = parts;
@@ -829,12 +829,15 @@ static int launch_afb_owner_t(const AfbOwnerParams& op, cudaStream_t st) {
         for (int q = 0; q < op.parts; ++q) rows = std::max(rows, op.ol[j].c1[q] - op.ol[j].c0[q]);
         floats = std::max(floats, (size_t)op.ring_floats + op.map_ints + op.ol[j].buf_off + (size_t)rows * op.ol[j].pitch);
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the attribute is per device: a process may drive several GPUs
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         const cudaError_t e = cudaFuncSetAttribute(afb_owner_kernel<L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    (int)kOwnerSmemMax);
         if (e != cudaSuccess) return set_last_cuda_error(e);
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
 #ifdef B200W_TIMELINE
     static unsigned long long* tl = nullptr;

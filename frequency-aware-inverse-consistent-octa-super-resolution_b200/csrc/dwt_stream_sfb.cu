@@ -565,10 +565,10 @@ static bool sfb_owner_plan_t(const SfbParams& p, int sms, bool force, SfbOwnerPa
     if (PER) parts = 1;   // the coefficient rows wrap around: a part would need rows from the far end
     parts = std::min(parts, p.lv[J - 1].out_h);
     if (!force) {
-        // one CTA per SM: too few CTAs leave the device idle (the chain kernels spread better), and a short last
-        // wave wastes up to half of the time
+        // one CTA per SM: a short last wave wastes up to half of the time (few CTAs are fine: small batches are
+        // latency-bound either way, and measured faster here than as ticketed chains, profiles/r01_smallbatch.log)
         const long long ctas = (long long)p.planes * parts, waves = (ctas + sms - 1) / sms;
-        if (ctas < sms / 2 || ctas * 4 < waves * sms * 3) return false;
+        if (ctas * 4 < waves * sms * 3 && waves > 1) return false;
     }
     op.p = p;
     op.parts = parts;
@@ -648,12 +648,15 @@ template <int L, bool PER>
 static int launch_sfb_owner_t(const SfbOwnerParams& op, cudaStream_t st) {
     constexpr int NT = SfbOwnerCfg<L>::NT;
     constexpr int S2V = sfb_shift2(L, PER);
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the attribute is per device: a process may drive several GPUs
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         const cudaError_t e = cudaFuncSetAttribute(sfb_owner_kernel<L, S2V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    (int)kSfbOwnerSmemMax);
         if (e != cudaSuccess) return set_last_cuda_error(e);
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     const size_t smem = ((size_t)op.ring_floats + op.y_floats) * 4;
 #ifdef B200W_TIMELINE
