@@ -126,6 +126,7 @@ __device__ __forceinline__ void sfb_ring_cta(const SfbParams& p, const SfbLevel&
     const float* hicol = has_hi ? lv.highs + (size_t)plane * 3 * band + kb : lowcol;
     float2* ring = ring_all + (size_t)(tid >> 5) * D * C::STAGE;
     const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring) + (unsigned)slot * 8u;
+    const bool vec2 = lv.vec2 != 0;   // V == 0: copy width chosen at run time (same window geometry either way)
 
     // stage coefficient row q of this lane's segment into ring stage `st`.  Rows inside the sub-band take the
     // plain cp.async (the zero-filling form costs three padding instructions each); zero rows and a missing
@@ -140,7 +141,7 @@ __device__ __forceinline__ void sfb_ring_cta(const SfbParams& p, const SfbLevel&
                 const unsigned dst = ring_s + (unsigned)((st * 4 + b) * C::RPB) * 8u;
                 if (sr >= 0 && (b == 0 || has_hi)) {
                     const float* src = b == 0 ? lowcol + (long long)sr * low_rs : hicol + (size_t)(b - 1) * band + (size_t)sr * w;
-                    if (V == 2) {
+                    if (V == 2 || (V == 0 && vec2)) {
                         cp_async<2>(dst, src);
                         if (run_last) {
 #pragma unroll
@@ -219,7 +220,7 @@ __device__ __forceinline__ void sfb_ring_cta(const SfbParams& p, const SfbLevel&
                     for (int k = 0; k < NS; ++k) {
                         float2 v = make_float2(0.f, 0.f);
                         if (sr >= 0) {
-                            if (V == 2) {
+                            if (V != 1) {   // V == 0: the window start is even whichever way the rows were staged
                                 v = lds64(a + 8u * k);
                             } else {
                                 v.x = lds32(a + 8u * k);
@@ -402,7 +403,10 @@ __global__ void __launch_bounds__(kStreamNT, SfbStreamCfg<L, S2V>::MINB) sfb_str
     const SfbOwnRows none{};
     if (cta < lv.cppA) {
         const int it = cta * kStreamNT + tid;
-        if (lv.vec2) sfb_ring_cta<L, 2, S2V>(p, lv, plane, it, sfb_ring_all, wait_ctr, wait_need, none);
+        // without a shift the 64-bit and the 32-bit staged windows coincide: one code path picks the copy width at
+        // run time (half the code in the instruction cache); periodization shifts the 64-bit window by one
+        if (S2V == 0) sfb_ring_cta<L, 0, 0>(p, lv, plane, it, sfb_ring_all, wait_ctr, wait_need, none);
+        else if (lv.vec2) sfb_ring_cta<L, 2, S2V>(p, lv, plane, it, sfb_ring_all, wait_ctr, wait_need, none);
         else sfb_ring_cta<L, 1, 0>(p, lv, plane, it, sfb_ring_all, wait_ctr, wait_need, none);
     } else {
         const int it = (cta - lv.cppA) * kStreamNT + tid;
@@ -484,10 +488,12 @@ __global__ void __launch_bounds__(SfbOwnerCfg<L>::NT, 1) sfb_owner_kernel(const 
             __syncwarp();   // the warp's ring is reused from pass to pass
             const int it = base + tid;
             if (smem_low) {
-                if (lv.vec2) sfb_ring_cta<L, 2, S2V, true, true>(p, lv, plane, it, sfb_ring_all, nullptr, 0u, own);
+                if (S2V == 0) sfb_ring_cta<L, 0, 0, true, true>(p, lv, plane, it, sfb_ring_all, nullptr, 0u, own);
+                else if (lv.vec2) sfb_ring_cta<L, 2, S2V, true, true>(p, lv, plane, it, sfb_ring_all, nullptr, 0u, own);
                 else sfb_ring_cta<L, 1, 0, true, true>(p, lv, plane, it, sfb_ring_all, nullptr, 0u, own);
             } else {
-                if (lv.vec2) sfb_ring_cta<L, 2, S2V, true, false>(p, lv, plane, it, sfb_ring_all, nullptr, 0u, own);
+                if (S2V == 0) sfb_ring_cta<L, 0, 0, true, false>(p, lv, plane, it, sfb_ring_all, nullptr, 0u, own);
+                else if (lv.vec2) sfb_ring_cta<L, 2, S2V, true, false>(p, lv, plane, it, sfb_ring_all, nullptr, 0u, own);
                 else sfb_ring_cta<L, 1, 0, true, false>(p, lv, plane, it, sfb_ring_all, nullptr, 0u, own);
             }
         }
