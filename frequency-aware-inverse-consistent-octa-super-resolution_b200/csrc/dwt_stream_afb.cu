@@ -412,7 +412,9 @@ __device__ __forceinline__ void afb_border_item(const AfbParams& p, const AfbLev
             const int jh = j0 + jj;
             const int sr = jh < L ? srow[jh < L ? jh : 0] : -1;
             rok[jj] = sr >= 0;
-            const float* rowp = xp + (long long)max(sr, 0) * lv.x_rs;
+            // a zero row is read from a row that exists (and discarded): row 0 of an owner CTA's shared-memory image
+            // would lie before the buffer
+            const float* rowp = xp + (long long)max(sr, OWNER ? own.src_row0 : 0) * lv.x_rs;
 #pragma unroll
             for (int j = 0; j < L; ++j) v[jj][j] = rowp[max(cidx[j], 0)];
         }

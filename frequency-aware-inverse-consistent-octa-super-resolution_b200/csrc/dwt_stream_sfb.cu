@@ -345,7 +345,7 @@ __device__ __forceinline__ void sfb_border_item(const SfbParams& p, const SfbLev
             const int uH = u0 + uu;
             const int kr = uH < H2 ? krow[uH < H2 ? uH : 0] : -1;
             rok[uu] = kr >= 0;
-            const int row = max(kr, 0);
+            const int row = max(kr, OWNER ? own.low_row0 : 0);   // a zero row is read from a row that exists
             const float* lp = lowp + (long long)row * lv.low_rs;
             const float* hp = hip + (size_t)row * w;
 #pragma unroll

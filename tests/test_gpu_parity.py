@@ -553,15 +553,24 @@ def test_patch_model_swaps_the_discriminator_methods():
     assert rel_err(got.cpu(), case["y"][0]) < RTOL_F32
 
 
+_OWNER_GRID = [((12, 1, 128, 160), w, m, 3) for w in ("haar", "db2", "db3", "db4", "db5", "db8")
+               for m in ("zero", "symmetric", "reflect", "periodic", "periodization")]
+
+
 @pytest.mark.parametrize("shape,wave,mode,J", [((64, 1, 76, 76), "db3", "symmetric", 3),
                                                ((160, 1, 50, 66), "db2", "reflect", 2),
                                                ((40, 2, 75, 83), "haar", "zero", 4),
                                                ((80, 1, 64, 96), "db4", "periodization", 3),
                                                ((37, 2, 61, 47), "db5", "periodic", 2),
-                                               ((64, 1, 304, 304), "db3", "symmetric", 3)])
+                                               ((16, 1, 256, 256), "db3", "zero", 3),
+                                               ((8, 1, 512, 384), "db2", "zero", 4),     # first level(s) as a chain launch
+                                               ((8, 1, 640, 512), "db4", "symmetric", 5),
+                                               ((24, 1, 128, 192), "db4", "zero", 2),
+                                               ((64, 1, 304, 304), "db3", "symmetric", 3)] + _OWNER_GRID)
 def test_owner_kernel_shapes(shape, wave, mode, J):
-    """Shapes the default policy hands to the owner kernel (many small planes, J > 1; parts of a plane overlap by the
-    rows the deeper levels need) against the oracle, forward and gradient."""
+    """Shapes the default policy hands to the owner kernel (small planes with 16-byte aligned rows, J > 1; parts of a
+    plane overlap by the rows the deeper levels need) against the oracle, forward, inverse and gradient -- including
+    every padding mode x filter length on one shape (zero rows / wrapped rows / long filters in every code path)."""
     rng = np.random.default_rng(J * 100 + shape[-1])
     xn = rng.standard_normal(shape).astype(np.float32)
     xfm = b200wave.DWTForward(J=J, wave=wave, mode=mode).to(DEV)
