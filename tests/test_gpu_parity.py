@@ -95,6 +95,9 @@ def _wave_taps(name):
     ("db1", 4, "zero", (2, 1, 128, 256)),
     ("db6", 2, "periodization", (1, 1, 96, 128)),
     ("db3", 2, "symmetric", (3, 1, 304, 304)),        # cfg2 geometry
+    ("db3", 3, "symmetric", (6, 1, 304, 304)),        # cfg2 itself: the inverse crops 80 -> 79 ('unpad'), its backward
+                                                      # runs the analysis chain over a zero-extended row / column
+    ("db2", 3, "zero", (5, 1, 300, 296)),             # crops at two levels, zero padding, through the owner kernels
     ("db7", 2, "periodization", (1, 1, 256, 132)),
 ])
 def test_oracle_dwt_roundtrip_seeded(wave, J, mode, shape):
