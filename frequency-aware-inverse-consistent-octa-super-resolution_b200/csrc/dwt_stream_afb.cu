@@ -778,6 +778,10 @@ static bool afb_owner_plan_t(const AfbParams& p, int sms, int j0_min, bool force
     }
     // start at the first level from which on the low-pass images fit next to the rings
     for (int j0 = j0_min; j0 <= J - 2; ++j0) {
+        // Starting behind a chain launch of the first level(s) is only taken when asked for (B200W_OWNER=2 /
+        // B200W_OWNER_J0): with big first levels the dependent ones are a few percent of the work, and their parts
+        // recompute more rows than they own (16 x 2048^2, J = 5: 172 vs 164 us for the plain chain)
+        if (j0 > 0 && !force && j0_min == 0) return false;
         size_t floats = 0;
         for (int j = j0; j < J - 1; ++j) {
             int rows = 0;
