@@ -200,6 +200,19 @@ int b200w_ssim_bwd_f32(const float* img1, const float* img2, const float* maps, 
                        const float* win, int ws, int size_average,
                        float* d1, float* d2, void* stream);
 
+/*
+ * Total-variation loss, model.py:17-33 (`TVLoss`, train.py:98), SURVEY.md 8f row 4.
+ * b200w_tv_fwd_f32: out2[0] = sum (x[i+1][j]-x[i][j])^2, out2[1] = sum (x[i][j+1]-x[i][j])^2 over all `planes`
+ * dense H x W planes, one pass over x; `workspace` = b200w_tv_workspace_bytes(planes, H) bytes of per-CTA partials
+ * (reduced in fixed order: deterministic).  The scalar loss is weight*2*(out2[0]/count_h + out2[1]/count_w)/batch.
+ * b200w_tv_bwd_f32: dx = grad_out[0] * (ch * d out2[0]/dx + cw * d out2[1]/dx); grad_out is a device scalar.
+ */
+size_t b200w_tv_workspace_bytes(int planes, int H);
+int b200w_tv_fwd_f32(const float* x, int planes, int H, int W, void* workspace, size_t workspace_bytes,
+                     float* out2, void* stream);
+int b200w_tv_bwd_f32(const float* x, const float* grad_out, float ch, float cw, int planes, int H, int W,
+                     float* dx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,3 +85,16 @@ def load_fsd_cases():
                                                   case["x"].shape[-2], case["x"].shape[-1])
         cases.append(case)
     return cases
+
+
+def load_tv_cases():
+    z = np.load(os.path.join(GOLDEN, "tv_cases.npz"))
+    cases = []
+    for i in range(int(z["ncases"])):
+        pre = "t%02d/" % i
+        case = {k[len(pre):]: z[k] for k in z.files if k.startswith(pre)}
+        case["weight"] = float(case["weight"])
+        case["loss"] = float(case["loss"])
+        case["id"] = "%02d-%s-w%g" % (i, "x".join(str(d) for d in case["x"].shape), case["weight"])
+        cases.append(case)
+    return cases

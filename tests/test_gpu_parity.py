@@ -13,9 +13,9 @@ import torch
 
 import b200wave
 from b200wave import lowlevel
-from oracle import dwt_oracle, freq_oracle, fsd_oracle, ssim_oracle
+from oracle import dwt_oracle, freq_oracle, fsd_oracle, ssim_oracle, tv_oracle
 from helpers import (RTOL_F32, case_filters, load_dwt_cases, load_freq_cases, load_fsd_cases, load_ssim_cases,
-                     rel_err)
+                     load_tv_cases, rel_err)
 
 pytestmark = pytest.mark.gpu
 
@@ -601,3 +601,36 @@ def test_owner_kernel_shapes(shape, wave, mode, J):
     for j in range(J - 1, -1, -1):
         d = dwt_oracle.afb2d_backward(d, gh[j].astype(np.float64), h[0], h[1], h[0], h[1], mode, sizes[j])
     assert rel_err(dx.cpu(), d) < RTOL_F32
+
+
+TV_CASES = load_tv_cases()
+
+
+@pytest.mark.parametrize("case", TV_CASES, ids=[c["id"] for c in TV_CASES])
+def test_golden_tv_loss(case):
+    """b200wave.losses.TVLoss vs the reference module's own value and input gradient (model.py:17-33)."""
+    from b200wave.losses import TVLoss
+    x = cu(case["x"], grad=True)
+    loss = TVLoss(case["weight"])(x)
+    assert loss.dim() == 0
+    assert abs(loss.item() - case["loss"]) <= RTOL_F32 * abs(case["loss"])
+    loss.backward()
+    assert rel_err(x.grad.cpu(), case["dx"]) < RTOL_F32
+
+
+def test_tv_loss_full_size_and_scaled_gradient():
+    """BASELINE-sized batch against the oracle; an upstream gradient other than 1; non-contiguous input."""
+    from b200wave.losses import TVLoss
+    rng = np.random.default_rng(2)
+    xn = rng.random((64, 1, 304, 304)).astype(np.float32)
+    x = cu(xn, grad=True)
+    crit = TVLoss()
+    loss = crit(x)
+    assert abs(loss.item() - tv_oracle.tv_loss(xn)) <= RTOL_F32 * tv_oracle.tv_loss(xn)
+    (loss * 3.0).backward()
+    assert rel_err(x.grad.cpu(), tv_oracle.tv_loss_backward(xn, 3.0)) < RTOL_F32
+    xt = cu(xn[:4]).transpose(2, 3)               # strided view
+    ref = tv_oracle.tv_loss(np.ascontiguousarray(xn[:4].transpose(0, 1, 3, 2)))
+    assert abs(float(crit(xt)) - ref) <= RTOL_F32 * ref
+    a = float(crit(cu(xn[:2])))
+    assert a == float(crit(cu(xn[:2])))            # fixed-order reduction: bit-reproducible

@@ -3,8 +3,9 @@
 import numpy as np
 import pytest
 
-from oracle import dwt_oracle, freq_oracle, fsd_oracle, ssim_oracle
-from helpers import load_dwt_cases, load_freq_cases, load_fsd_cases, load_ssim_cases, case_filters, rel_err
+from oracle import dwt_oracle, freq_oracle, fsd_oracle, ssim_oracle, tv_oracle
+from helpers import (load_dwt_cases, load_freq_cases, load_fsd_cases, load_ssim_cases, load_tv_cases, case_filters,
+                     rel_err)
 
 DWT_CASES = load_dwt_cases()
 SSIM_CASES = load_ssim_cases()
@@ -142,3 +143,22 @@ def test_filter_wavelet_host_logic_without_gpu():
     assert sorted(k for k in filt.state_dict()) == ["h0_col", "h0_row", "h1_col", "h1_row"]   # DWTForward's names
     with pytest.raises(RuntimeError, match="CUDA-only"):
         filt(torch.rand(1, 1, 8, 8))
+
+
+TV_CASES = load_tv_cases()
+
+
+@pytest.mark.parametrize("case", TV_CASES, ids=[c["id"] for c in TV_CASES])
+def test_tv_oracle_vs_reference(case):
+    """tv_oracle vs the value and input gradient of the reference's TVLoss (model.py:17-33)."""
+    assert abs(tv_oracle.tv_loss(case["x"], case["weight"]) - case["loss"]) <= 1e-12 * abs(case["loss"])
+    assert rel_err(tv_oracle.tv_loss_backward(case["x"], 1.0, case["weight"]), case["dx"]) < 1e-12
+
+
+def test_tv_loss_host_logic_without_gpu():
+    import torch
+    from b200wave.losses import TVLoss
+    crit = TVLoss(TVLoss_weight=0.5)
+    assert crit.TVLoss_weight == 0.5 and crit._tensor_size(torch.zeros(2, 3, 4, 5)) == 60
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        crit(torch.rand(1, 1, 8, 8))

@@ -150,3 +150,34 @@ if what in ("ssim", "all"):
     ssim_case(256, 400, 400)
     ssim_case(64, 1024, 1024)
     ssim_case(8, 304, 304)
+
+
+def tv_case(n, h, w):
+    """TVLoss (model.py:17-33): fused sums / gradient kernels vs the reference's slicing arithmetic in torch."""
+    from b200wave.losses import TVLoss
+    nsets = max(2, int(2 * 126e6 * 1.05 / (4 * n * h * w)) + 1)
+    xs = [torch.rand(n, 1, h, w, device=dev) for _ in range(nsets)]
+    crit = TVLoss()
+
+    def ref(x):
+        b, hx, wx = x.size(0), x.size(2), x.size(3)
+        ch, cw = x[:, :, 1:, :].numel() // b, x[:, :, :, 1:].numel() // b
+        h_tv = torch.pow(x[:, :, 1:, :] - x[:, :, :hx - 1, :], 2).sum()
+        w_tv = torch.pow(x[:, :, :, 1:] - x[:, :, :, :wx - 1], 2).sum()
+        return 2 * (h_tv / ch + w_tv / cw) / b
+
+    g = torch.ones((), device=dev)
+    with torch.no_grad():
+        t_f = timeit(lambda i: torch.ops.b200wave_losses.tv_sums(xs[i % nsets]), nsets)
+        t_b = timeit(lambda i: torch.ops.b200wave_losses.tv_grad(xs[i % nsets], g, 1e-6, 1e-6), nsets)
+        t_r = timeit(lambda i: ref(xs[i % nsets]), nsets)
+    px = n * h * w
+    print("tv %4dx%4dx%4d  sums %7.1f us %5.0f GB/s (%4.1f%%) | grad %7.1f us %5.0f GB/s (%4.1f%%) | torch forward (reference arithmetic) %7.1f us x%.1f" % (
+        n, h, w, t_f * 1e6, 4 * px / t_f / 1e9, 4 * px / t_f / 1e9 / PEAK * 100, t_b * 1e6, 8 * px / t_b / 1e9,
+        8 * px / t_b / 1e9 / PEAK * 100, t_r * 1e6, t_r / t_f), flush=True)
+
+
+if what in ("tv", "all"):
+    tv_case(8, 256, 256)
+    tv_case(64, 304, 304)
+    tv_case(64, 1024, 1024)
