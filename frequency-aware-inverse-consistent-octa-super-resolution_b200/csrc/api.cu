@@ -1,5 +1,6 @@
 // ABI bookkeeping: version, status names, last CUDA error (thread-local, diagnostics only).
 #include <atomic>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace b200w {
@@ -8,6 +9,14 @@ static thread_local int g_last_cuda_error = 0;
 int set_last_cuda_error(cudaError_t e) {
     g_last_cuda_error = (int)e;
     return B200W_ERR_LAUNCH;
+}
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200W_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
 }
 static std::atomic<unsigned long long> g_launches{0};
 static const char* g_log[kLaunchLog] = {nullptr};

@@ -118,6 +118,29 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Programmatic dependent launch: a kernel launched with launch_pdl() may start while its predecessor in the stream
+// is still running; it must call pdl_wait() before it touches global memory (reads of the predecessor's results, and
+// writes -- the allocator may have handed it memory the predecessor still reads).  pdl_trigger() in the predecessor
+// lets the dependent grid be scheduled as soon as every CTA has issued it (or exited).  Both are no-ops for plain launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+bool pdl_enabled();   // B200W_PDL=0 switches the attribute off
+
+template <typename Kernel, typename Params>
+inline cudaError_t launch_pdl(Kernel kernel, unsigned grid, unsigned block, size_t smem, cudaStream_t st, const Params& prm) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, prm);
+}
+
 int set_last_cuda_error(cudaError_t e);
 // diagnostics: counts the launch and remembers the kernel's name (b200w_kernel_launches / b200w_kernel_log)
 void note_launch(const char* kernel);

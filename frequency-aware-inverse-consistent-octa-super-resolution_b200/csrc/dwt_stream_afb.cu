@@ -522,6 +522,7 @@ __global__ void __launch_bounds__(AfbOwnerCfg<L>::NT, 1) afb_owner_kernel(const 
 #else
 #define OWN_MARK(slot, v) do { } while (0)
 #endif
+    pdl_trigger();   // the next kernel in the stream may be scheduled as SMs free up (it waits before touching memory)
     int* const maps = reinterpret_cast<int*>(reinterpret_cast<float*>(ring_all) + op.ring_floats);
     float* const ll_area = reinterpret_cast<float*>(maps) + op.map_ints;
     // extension maps of every level, built once: input rows 2*c0 - offH + [0, 2*nrows + L) and input columns
@@ -545,6 +546,7 @@ __global__ void __launch_bounds__(AfbOwnerCfg<L>::NT, 1) afb_owner_kernel(const 
             m_out[e] = m;
         }
     }
+    pdl_wait();      // everything above used only the parameter block; from here on global memory is touched
     __syncthreads();
     OWN_MARK(13, (unsigned long long)clock64());
 #pragma unroll 1
@@ -855,9 +857,9 @@ static int launch_afb_owner_t(const AfbOwnerParams& op, cudaStream_t st) {
         cudaMemcpyToSymbolAsync(g_timeline, &tl, sizeof(tl), 0, cudaMemcpyHostToDevice, st);
     }
 #endif
-    afb_owner_kernel<L, S><<<(unsigned)(op.p.planes * op.parts), NT, floats * 4, st>>>(op);
+    const cudaError_t le = launch_pdl(afb_owner_kernel<L, S>, (unsigned)(op.p.planes * op.parts), NT, floats * 4, st, op);
     note_launch("afb_owner_kernel");
-    const cudaError_t e = cudaGetLastError();
+    const cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();
 #ifdef B200W_TIMELINE
     if (tl_path && ncta <= 65536) {
         cudaStreamSynchronize(st);

@@ -446,6 +446,8 @@ __global__ void __launch_bounds__(SfbOwnerCfg<L>::NT, 1) sfb_owner_kernel(const 
     const int plane = blockIdx.x / op.parts;
     const int part = blockIdx.x - plane * op.parts;
     float* const y_area = reinterpret_cast<float*>(sfb_ring_all) + op.ring_floats;
+    pdl_trigger();   // see afb_owner_kernel
+    pdl_wait();
 #ifdef B200W_TIMELINE
     // slot 0 / 14: %globaltimer at start / end; slot 15: clock at start; slots 1 + 3*c + {0,1,2}: clock after the
     // set-up, the interior passes and the border passes of chain position c
@@ -675,9 +677,9 @@ static int launch_sfb_owner_t(const SfbOwnerParams& op, cudaStream_t st) {
         cudaMemcpyToSymbolAsync(g_sfb_timeline, &tl, sizeof(tl), 0, cudaMemcpyHostToDevice, st);
     }
 #endif
-    sfb_owner_kernel<L, S2V><<<(unsigned)(op.p.planes * op.parts), NT, smem, st>>>(op);
+    const cudaError_t le = launch_pdl(sfb_owner_kernel<L, S2V>, (unsigned)(op.p.planes * op.parts), NT, smem, st, op);
     note_launch("sfb_owner_kernel");
-    const cudaError_t e = cudaGetLastError();
+    const cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();
 #ifdef B200W_TIMELINE
     if (tl_path && ncta <= 65536) {
         cudaStreamSynchronize(st);
