@@ -150,7 +150,7 @@ def cpu_reference(workload, steps, warmup, budget_s=60.0):
     cfg = WORKLOADS[workload]
     rng = np.random.default_rng(0)
     n, c, h, w = cfg["shape"]
-    cores = c_port.num_threads()
+    cores = c_port.use_all_cores()   # not OMP_NUM_THREADS: torchrun pins that to 1 for its workers
 
     if cfg["kind"] == "dwt":
         wv = pywt.Wavelet(cfg["wave"])

@@ -30,6 +30,15 @@ int ref_num_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline asks for the cores it may use explicitly */
+void ref_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 static int ext_index(int s, int n, int mode) {
     if (s >= 0 && s < n) return s;
     int p, m;

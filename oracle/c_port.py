@@ -39,6 +39,21 @@ def num_threads():
     return int(load().ref_num_threads())
 
 
+def use_all_cores():
+    """Let the port use every core this process may run on (torchrun sets OMP_NUM_THREADS=1 for its workers, which
+    would otherwise turn the all-cores CPU baseline into a single-thread one).  Returns the thread count."""
+    import os
+    lib = load()
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib.ref_set_num_threads.argtypes = [ctypes.c_int]
+    lib.ref_set_num_threads.restype = None
+    lib.ref_set_num_threads(int(n))
+    return num_threads()
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(_fp)
 
