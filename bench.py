@@ -214,6 +214,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
+    ap.add_argument("--fused-e2e", action="store_true",
+                    help="e2e: one captured graph per chunk (copies + kernels) instead of separate stream / event / "
+                         "copy calls (measured slower: the chunks' copies and kernels serialise inside each graph)")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="batch chunks of the host-buffer pipeline (e2e)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -380,7 +383,7 @@ def main():
     from b200wave import HostPipeline
     host_in = [tuple(t.detach().cpu().pin_memory().requires_grad_(t.requires_grad) for t in s) for s in sets[:2]]
     chunks = 1 if cfg["kind"] == "ssim" else args.e2e_chunks   # a scalar mean does not split into chunks
-    pipe = HostPipeline(step, host_in[0], chunks=chunks, graph=not args.no_graph)
+    pipe = HostPipeline(step, host_in[0], chunks=chunks, graph=not args.no_graph, fused=args.fused_e2e)
     h2d, d2h = pipe.bytes_per_call(host_in[0])
 
     def e2e_step(i):
@@ -507,8 +510,8 @@ def main():
             "step_hbm_frac": (step_bytes / (step_ms * 1e-3) / 1e9) / peak,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
-                    "api": "b200wave.HostPipeline(step, chunks=%d): pinned host -> H2D | kernels | D2H overlapped "
-                           "on three streams" % len(pipe.bounds)},
+                    "api": "b200wave.HostPipeline(step, chunks=%d%s): pinned host -> H2D | kernels | D2H overlapped "
+                           "on three streams" % (len(pipe.bounds), ", fused=True" if pipe.fused else "")},
             "gpu_launches": my_kernels_per_step * args.steps, "step_kernels": step_kernels,
             "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks,
         }

@@ -365,9 +365,9 @@ def test_host_pipeline_matches_direct_call():
     gh = torch.randn(10, 1, 76, 76).pin_memory()
     xd = xh.detach().to(DEV).requires_grad_(True)
     rec_ref, dx_ref = step(xd, gh.to(DEV))
-    for chunks, graph in [(1, False), (3, False), (4, True)]:
-        pipe = b200wave.HostPipeline(step, (xh, gh), chunks=chunks, graph=graph)
-        for _ in range(2):   # second call exercises buffer reuse
+    for chunks, graph, fused in [(1, False, False), (3, False, False), (4, True, False), (4, True, True), (5, True, True)]:
+        pipe = b200wave.HostPipeline(step, (xh, gh), chunks=chunks, graph=graph, fused=fused)
+        for _ in range(2):   # second call exercises buffer reuse (and, fused, the cached graphs)
             rec, dx = pipe((xh, gh))
         assert rec.shape == rec_ref.shape and dx.shape == dx_ref.shape
         assert rel_err(rec, rec_ref.detach().cpu()) < 1e-6
