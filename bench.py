@@ -217,7 +217,9 @@ def main():
     ap.add_argument("--fused-e2e", action="store_true",
                     help="e2e: one captured graph per chunk (copies + kernels) instead of separate stream / event / "
                          "copy calls (measured slower: the chunks' copies and kernels serialise inside each graph)")
-    ap.add_argument("--e2e-chunks", type=int, default=4, help="batch chunks of the host-buffer pipeline (e2e)")
+    ap.add_argument("--e2e-chunks", type=int, default=1,
+                    help="batch chunks of the host-buffer pipeline (e2e); consecutive steps already overlap their "
+                         "uploads and downloads, and one chunk per step measured best (profiles/r01_notes.md)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
