@@ -21,7 +21,7 @@ LIB_DIR = os.path.join(PKG_DIR, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libb200wave.so")
 STAMP = os.path.join(LIB_DIR, "libb200wave.stamp")
 
-SOURCES = ["api.cu", "dwt.cu", "dwt_stream_afb.cu", "dwt_stream_sfb.cu", "dwt_plane.cu", "ssim.cu", "freq.cu", "tv.cu"]
+SOURCES = ["api.cu", "dwt.cu", "dwt_stream_afb.cu", "dwt_stream_sfb.cu", "dwt_tma_afb.cu", "ssim.cu", "freq.cu", "tv.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -29,7 +29,7 @@ NVCC_FLAGS = [
     "-cudart", "static",
 ] + (["-DB200W_TIMELINE"] if os.environ.get("B200W_TIMELINE") == "1" else []) \
   + (["-DB200W_OWNER_NT=%d" % int(os.environ["B200W_OWNER_NT"])] if os.environ.get("B200W_OWNER_NT") else []) \
-  + (["-DB200W_OWNER_Q=%d" % int(os.environ["B200W_OWNER_Q"])] if os.environ.get("B200W_OWNER_Q") else [])
+  + ["-D" + d for d in os.environ.get("B200W_DEFINES", "").split()]
 
 
 def find_nvcc():
@@ -85,6 +85,8 @@ def _build_locked(nvcc, verbose):
     for src in SOURCES:
         obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
         cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
+        if src == "api.cu":   # the binary carries the hash of the tree it was built from (b200w_build_hash)
+            cmd.insert(1, '-DB200W_BUILD_HASH="%s"' % _source_hash())
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)

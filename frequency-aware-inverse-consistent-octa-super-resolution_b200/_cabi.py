@@ -52,6 +52,7 @@ SYMBOLS = {
     "b200w_tv_bwd_f32": (_i, [_vp, _vp, ctypes.c_float, ctypes.c_float, _i, _i, _i, _vp, _vp]),
     "b200w_kernel_launches": (ctypes.c_ulonglong, []),
     "b200w_kernel_log": (ctypes.c_char_p, [_i]),
+    "b200w_build_hash": (ctypes.c_char_p, []),
     "b200w_dwt2_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i, _c_int_p]),
     "b200w_dwt2_f32": (_i, [_vp, _i64, _i64, _i, _i, _i,
                             _c_float_p, _c_float_p, _i, _c_float_p, _c_float_p, _i,
@@ -92,6 +93,12 @@ def load(build_if_missing=True):
         if path == _build.LIB_PATH and build_if_missing and not _build.is_fresh():
             if _build.find_nvcc() is not None:
                 _build.build()
+            elif os.path.exists(path):
+                # *.so is git-ignored but travels to the GPU boxes: never let a stale binary pass silently
+                import warnings
+                warnings.warn("libb200wave.so does not match the sources in this tree and nvcc is not available to "
+                              "rebuild it; results come from the OLD binary (see b200wave._cabi.build_hash())",
+                              RuntimeWarning, stacklevel=2)
         if not os.path.exists(path):
             raise B200WaveError(
                 "libb200wave.so not found at %s and nvcc is unavailable to build it. This package has no "
@@ -105,6 +112,14 @@ def load(build_if_missing=True):
             raise B200WaveError("libb200wave ABI version %d != expected %d" % (lib.b200w_abi_version(), ABI_VERSION))
         _lib = lib
     return _lib
+
+
+def build_hash():
+    """{"library": hash the loaded binary was built from, "tree": hash of the sources here, "match": bool}."""
+    lib = load()
+    have = lib.b200w_build_hash().decode()
+    want = _build._source_hash() if library_path() == _build.LIB_PATH else None
+    return {"library": have[:16], "tree": None if want is None else want[:16], "match": want is None or have == want}
 
 
 def status_string(code):

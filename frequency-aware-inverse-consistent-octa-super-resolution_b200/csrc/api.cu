@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdlib>
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace b200w {
 constexpr int kLaunchLog = 64;
@@ -18,6 +19,44 @@ bool pdl_enabled() {
     }
     return v == 1;
 }
+EncodeTiledFn tma_encode_fn() {
+    static std::atomic<void*> fn{nullptr};
+    static std::atomic<int> state{0};   // 0 = not looked up, 1 = found, 2 = unavailable
+    if (state.load(std::memory_order_acquire) == 0) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres = cudaDriverEntryPointSymbolNotFound;
+        const cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+        if (e != cudaSuccess) (void)cudaGetLastError();
+        const bool ok = e == cudaSuccess && qres == cudaDriverEntryPointSuccess && p != nullptr;
+        fn.store(ok ? p : nullptr, std::memory_order_relaxed);
+        state.store(ok ? 1 : 2, std::memory_order_release);
+    }
+    return reinterpret_cast<EncodeTiledFn>(fn.load(std::memory_order_relaxed));
+}
+
+bool tma_make_map_f32(CUtensorMap* map, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box) {
+    EncodeTiledFn enc = tma_encode_fn();
+    if (!enc || rank < 1 || rank > 4) return false;
+    cuuint64_t gdim[4], gstr[4];
+    cuuint32_t bdim[4], estr[4];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bdim[i] = box[i];
+        estr[i] = 1;
+        if (box[i] < 1 || box[i] > 256 || dims[i] < 1) return false;
+    }
+    for (int i = 0; i + 1 < rank; ++i) {
+        gstr[i] = strides_bytes[i];
+        if ((gstr[i] & 15) != 0 || gstr[i] == 0) return false;
+    }
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((size_t)box[0] * 4) % 16 != 0) return false;
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), gdim, gstr,
+                           bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 static std::atomic<unsigned long long> g_launches{0};
 static const char* g_log[kLaunchLog] = {nullptr};
 void note_launch(const char* kernel) {
@@ -34,6 +73,11 @@ extern "C" const char* b200w_kernel_log(int back) {
     const char* s = b200w::g_log[(n - 1 - (unsigned long long)back) % b200w::kLaunchLog];
     return s ? s : "";
 }
+
+#ifndef B200W_BUILD_HASH
+#define B200W_BUILD_HASH "unknown"
+#endif
+extern "C" const char* b200w_build_hash(void) { return B200W_BUILD_HASH; }
 
 extern "C" int b200w_abi_version(void) { return B200W_ABI_VERSION; }
 

@@ -25,6 +25,7 @@
 // per pixel low -- 128-bit shared loads feeding register-blocked FMAs whose coefficients come from the
 // constant bank, 64-bit coalesced global stores, staging loops whose addresses advance by constants.
 #include "dwt_levels.cuh"
+#include "dwt_tma.cuh"
 
 namespace b200w {
 
@@ -653,15 +654,6 @@ static bool force_tiled() {
     if (v < 0) v = env_flag("B200W_FORCE_TILED");
     return v == 1;
 }
-// B200W_PLANE=1: run the levels whose planes fit in shared memory with the plane-resident kernels (dwt_plane.cu).
-// Off by default: as measured in round 1 (profiles/r01_notes.md) they are instruction-bound and only match the
-// chain kernels; they stay in the tree as a third, independently written implementation that the parity tests
-// cross-check, and as the starting point for fusing the small levels.
-static bool no_plane() {
-    static int v = -1;
-    if (v < 0) v = env_flag("B200W_PLANE");
-    return v != 1;
-}
 // B200W_OWNER=0 switches the owner kernels off (chains of small planes then take the ticketed chain kernels);
 // B200W_OWNER_J0=n makes them start no earlier than level n (the levels before run as a chain launch).
 // B200W_OWNER=2 uses them whenever the shapes fit, however few planes there are (tests).
@@ -969,8 +961,13 @@ static int run_afb_chain(const float* x, int64_t x_ps, int64_t x_rs, int planes,
     }
     // the store epilogue lives in the stream and the direct kernels: other inputs (unaligned rows) take the direct one
     if (templated_taps(Lw, Lh) && (plain || (!force_tiled() && afb_stream_supported(p, Lw)))) {
-        // levels whose input plane fits in shared memory run plane-resident (one launch for all of them); the
-        // bigger levels before them go through the stream chain (or the tile chain when rows are unaligned)
+        // chains of small planes: one CTA owns a part of a plane for all levels (TMA-staged owner kernel first, the
+        // cp.async owner kernel for the shapes it declines); everything else goes through the ticketed stream chain
+        // (or the tile chain when rows are unaligned)
+        if (J > 1 && plain && !force_tiled() && owner_mode() != 0) {
+            AfbTmaParams tp;
+            if (afb_tma_plan(p, Lw, device_info().sms, owner_mode() == 2, tp)) return launch_afb_tma(tp, Lw, st);
+        }
         if (J > 1 && !force_tiled() && owner_mode() != 0) {
             AfbOwnerParams op;
             if (afb_owner_plan(p, Lw, device_info().sms, owner_j0_min(), owner_mode() == 2, op)) {
@@ -982,16 +979,6 @@ static int run_afb_chain(const float* x, int64_t x_ps, int64_t x_rs, int planes,
                 }
                 return launch_afb_owner(op, Lw, st);
             }
-        }
-        int first = (force_tiled() || no_plane() || !plain) ? J : afb_plane_first(p, Lw);
-        if (first < J) {
-            if (first > 0) {
-                AfbParams head = p;
-                head.J = first;
-                rc = run_afb_big_levels(head, Lw, st);
-                if (rc) return rc;
-            }
-            return launch_afb_plane(p, Lw, first, st);
         }
         return run_afb_big_levels(p, Lw, st);
     }
@@ -1109,20 +1096,9 @@ static int run_sfb_chain(const float* yl, int64_t yl_ps, int64_t yl_rs, const fl
         lv.y_vec = 1;
     }
     if (templated_taps(Lw, Lh)) {
-        // the coarse levels whose planes fit in shared memory run plane-resident (one launch), the finer ones after
-        // them through the stream chain (or the tile chain)
         if (J > 1 && !force_tiled() && owner_mode() != 0) {
             SfbOwnerParams op;
             if (sfb_owner_plan(p, Lw, device_info().sms, owner_mode() == 2, op)) return launch_sfb_owner(op, Lw, st);
-        }
-        const int count = (force_tiled() || no_plane()) ? 0 : sfb_plane_count(p, Lw);
-        if (count > 0) {
-            rc = launch_sfb_plane(p, Lw, count, st);
-            if (rc || count == J) return rc;
-            SfbParams tail = p;
-            for (int c = count; c < J; ++c) tail.lv[c - count] = p.lv[c];
-            tail.J = J - count;
-            return run_sfb_big_levels(tail, Lw, st);
         }
         return run_sfb_big_levels(p, Lw, st);
     }

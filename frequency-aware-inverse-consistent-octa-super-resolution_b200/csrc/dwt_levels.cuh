@@ -71,10 +71,6 @@ struct AfbParams {
 // the CTA's shared memory, so the dependent levels cost a block barrier instead of a trip through L2 and a
 // grid-wide dependency.  Parts of a plane overlap by the few rows the deeper levels need (recomputed, not shared).
 constexpr int kMaxParts = 8;
-#ifndef B200W_OWNER_Q
-#define B200W_OWNER_Q 1      // column pairs per lane of the analysis owner kernel for filters up to 6 taps (2 was measured: 9 % fewer
-                             // instructions per pixel, but shorter segments with a larger warm-up share: 24.6 vs 20.1 us at cfg2)
-#endif
 #ifndef B200W_OWNER_NT
 #define B200W_OWNER_NT 384   // threads of an owner CTA for filters up to 8 taps: 12 warps with up to 168 registers each (measured best of 256..512, profiles/r01_notes.md)
 #endif
@@ -159,14 +155,6 @@ int launch_afb_owner(const AfbOwnerParams& op, int L, cudaStream_t st);
 // outputs in shared memory
 bool sfb_owner_plan(const SfbParams& p, int L, int sms, bool force, SfbOwnerParams& op);
 int launch_sfb_owner(const SfbOwnerParams& op, int L, cudaStream_t st);
-
-// plane-resident kernels (dwt_plane.cu): one CTA per plane runs the small levels of a transform in shared memory.
-// afb_plane_first = first analysis level from which on the rest fits (p.J = none); sfb_plane_count = number of
-// leading (coarse) synthesis chain positions that fit (0 = none).
-int afb_plane_first(const AfbParams& p, int L);
-int launch_afb_plane(const AfbParams& p, int L, int first, cudaStream_t st);
-int sfb_plane_count(const SfbParams& p, int L);
-int launch_sfb_plane(const SfbParams& p, int L, int count, cudaStream_t st);
 
 // clears the ticket + completion counters of a chain on the stream (a kernel rather than a memset node: inside a
 // CUDA graph a kernel -> memset -> kernel sequence costs several microseconds of engine switching)

@@ -502,7 +502,7 @@ struct AfbOwnerCfg {
     // one CTA per SM; long filters need more than 128 registers per thread
     static constexpr int NT = L <= 8 ? B200W_OWNER_NT : 256;
     // column pairs per lane: two for the short filters (their accumulators fit the register budget twice)
-    static constexpr int Q = L <= 6 ? B200W_OWNER_Q : 1;
+    static constexpr int Q = 1;
 };
 
 template <int L, int S>

@@ -1,0 +1,65 @@
+// Parameter blocks of the TMA-staged owner kernels (dwt_tma_afb.cu / dwt_tma_sfb.cu).
+//
+// One CTA owns a horizontal part of one image plane for EVERY level of a multi-level transform (as the round-1 owner
+// kernels did), but the rows it streams from global memory arrive through the copy engine: one elected producer lane
+// per row stream issues cp.async.bulk.tensor tiles (several full-width rows per instruction) into an mbarrier-guarded
+// ring, a patch warp writes the few extension columns of the padding mode next to the landed rows, and every consumer
+// lane then runs the same border-free register march over 16-byte aligned shared-memory windows.  The intermediate
+// low-pass images (analysis) / partial reconstructions (synthesis) stay in shared memory, stored WITH their extension
+// columns, so the dependent levels have no border class either.
+#pragma once
+#include "dwt_levels.cuh"
+#include "tma.cuh"
+
+namespace b200w {
+
+constexpr int kTmaMaxStreams = 8;    // row streams (segments of the streamed level) per CTA
+constexpr int kTmaMaxStrips = 4;     // tiles per staged row (a tile is at most 256 floats wide)
+
+// taps of the templated kernels (<= 16), W taps as constant-bank scalars, H taps once more as (t, t) pairs for FFMA2
+struct TapsT {
+    float w_lo[kMaxTemplTaps], w_hi[kMaxTemplTaps];
+    float2 h_lo2[kMaxTemplTaps], h_hi2[kMaxTemplTaps];
+};
+
+struct AfbTmaLevel {
+    float* low;            // global low-pass output (last level only)
+    float* highs;          // global (planes, 3, Ho, Wo)
+    int H, W;              // logical input size (including the zero extension of SFB2D.backward's 'unpad')
+    int Hreal, Wreal;      // rows / columns >= these read as zero
+    int Ho, Wo;
+    int ncp;               // output column pairs = ceil(Wo / 2)
+    int R, nseg;           // output rows per segment, segments (level 0: = row streams)
+    int in_pitch;          // level >= 1: row pitch (floats, multiple of 4) of the input image in shared memory
+    int in_off;            // level >= 1: byte offset of that image from the dynamic shared-memory base
+    int in_rows;           // level >= 1: rows of that image (max over the parts)
+    int rtab_off;          // int offset of the row table of this level's input rows inside the table area
+    int cfix_off;          // level >= 1: int offset of the column-patch table (pairs dst, src) and of its counter
+    int vec2, low_vec2;    // 64-bit global stores allowed
+    int c0[kMaxParts], c1[kMaxParts];   // output rows a part computes
+    int h0[kMaxParts], h1[kMaxParts];   // output rows a part stores to global memory (a partition of [0, Ho))
+};
+
+struct AfbTmaParams {
+    CUtensorMap map_full;  // level-0 input (W, H, planes), box {BW, SR, 1}
+    CUtensorMap map_row;   // the same tensor, box {BW, 1, 1}: rows the padding mode maps somewhere else
+    AfbTmaLevel lv[kMaxLevels];
+    TapsT t;
+    int J, planes, parts, mode;
+    int D, nstrips, cps, BW;   // ring: stages, tiles per row, column pairs per tile, tile width (floats, multiple of 32)
+    int fix0_off, fix0_n;      // int offset of the ring's column-patch table (int2 per stage row x extension column) and
+                               // the extension columns per stage row
+    int dbg;                   // debug (B200W_TMA_DBG): 1 = consumers do not wait for the data, 2 = consumers skip the arithmetic
+    unsigned long long* timeline;   // debug (B200W_TMA_TIMELINE=file): per-CTA clock stamps, else null
+    int bar_off, tab_off, zrow_off, ring_off;   // shared-memory layout (bytes from the dynamic base)
+    int zrow_floats, tab_ints;
+    int smem_bytes;
+};
+static_assert(sizeof(AfbTmaParams) <= 4096, "kernel parameter block");
+
+// planning + launch (dwt_tma_afb.cu).  afb_tma_plan returns false when the shapes do not qualify (unaligned rows, the
+// low-pass images do not fit, the driver has no tensor-map entry point, ...): the caller then takes the other kernels.
+bool afb_tma_plan(const AfbParams& p, int L, int sms, bool force, AfbTmaParams& tp);
+int launch_afb_tma(const AfbTmaParams& tp, int L, cudaStream_t st);
+
+}  // namespace b200w

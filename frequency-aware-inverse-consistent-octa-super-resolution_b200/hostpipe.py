@@ -9,13 +9,6 @@ what the end-to-end number of ``bench.py`` measures.
     pipe = HostPipeline(step, example_inputs=(x_host, g_host), chunks=4)
     rec_host, dx_host = pipe((x_host, g_host))
 
-With ``fused=True`` the copies are captured too: every chunk becomes ONE CUDA graph (upload -> kernels -> download)
-replayed round-robin on three streams, so a call costs one graph launch per chunk on the host instead of a dozen
-stream / event / copy calls.  Measured on B200 boxes it is not faster (cfg2: 1.44 vs 1.26 ms per step on the same
-box): the host loop is not the limit, and inside a chunk's graph upload, kernels and download run back to back; it is
-kept as an option for hosts with slow Python enqueue.  The graphs hold the addresses of the pinned input tensors they were captured with; they
-are cached per set of input tensors (by address), so callers should cycle through a few fixed pinned buffers.
-
 ``step(*device_inputs) -> tuple of device tensors`` is called once per chunk (and captured into one CUDA graph per
 chunk when ``graph=True``, so the per-chunk launch cost is a graph replay).  Outputs whose leading dimension is
 the chunk's batch size are written to the matching rows of the pinned result; other outputs (e.g. a scalar
@@ -35,7 +28,7 @@ def _chunk_bounds(n, chunks):
 
 
 class HostPipeline(object):
-    def __init__(self, step, example_inputs, chunks=4, graph=True, device=None, fused=False):
+    def __init__(self, step, example_inputs, chunks=4, graph=True, device=None):
         if not torch.cuda.is_available():
             raise RuntimeError("HostPipeline needs a CUDA device (there is no CPU fallback)")
         self.step = step
@@ -72,10 +65,6 @@ class HostPipeline(object):
                     self.dev_out[k] = outs
         cur.wait_stream(self.s_run)
         self.host_out = None
-        self.fused = bool(fused) and bool(graph)
-        self.fused_streams = [self.s_in, self.s_run, self.s_out]
-        self.fused_graphs = {}     # addresses of the pinned inputs -> one graph per chunk
-        self.fused_keep = {}       # keeps those input tensors alive while their graphs exist
 
     def _call(self, ins):
         for t in ins:
@@ -104,53 +93,7 @@ class HostPipeline(object):
 
     def join(self):
         """Make the current stream wait for every result copy issued so far (device-side; does not block the host)."""
-        cur = torch.cuda.current_stream(self.device)
-        if self.fused:
-            for s in self.fused_streams:
-                cur.wait_stream(s)
-        else:
-            cur.wait_stream(self.s_out)
-
-    def _capture_fused(self, host_inputs):
-        """One graph per chunk: H2D of the chunk's inputs, the step, D2H of its results."""
-        graphs = []
-        for s in self.fused_streams:
-            s.synchronize()
-        for k, (lo, hi) in enumerate(self.bounds):
-            st = self.fused_streams[k % len(self.fused_streams)]
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=st):
-                with torch.no_grad():
-                    for d, s in zip(self.dev_in[k], host_inputs):
-                        d.copy_(s[lo:hi], non_blocking=True)
-                outs = self._call(self.dev_in[k])
-                for (h, per_sample), o in zip(self.host_out, outs):
-                    (h[lo:hi] if per_sample else h[k]).copy_(o, non_blocking=True)
-            graphs.append((g, outs))
-        return graphs
-
-    def _call_fused(self, host_inputs, sync):
-        key = tuple(t.data_ptr() for t in host_inputs)
-        graphs = self.fused_graphs.get(key)
-        cur = torch.cuda.current_stream(self.device)
-        if graphs is None:
-            if len(self.fused_graphs) >= 8:      # callers are expected to cycle through a few pinned buffers
-                old = next(iter(self.fused_graphs))
-                del self.fused_graphs[old], self.fused_keep[old]
-            graphs = self._capture_fused(host_inputs)
-            self.fused_graphs[key] = graphs
-            self.fused_keep[key] = tuple(host_inputs)
-        if sync:
-            for s in self.fused_streams:
-                s.wait_stream(cur)
-        for k, (g, _) in enumerate(graphs):
-            with torch.cuda.stream(self.fused_streams[k % len(self.fused_streams)]):
-                g.replay()
-        if sync:
-            for s in self.fused_streams:
-                cur.wait_stream(s)
-                s.synchronize()
-        return tuple(h for h, _ in self.host_out)
+        torch.cuda.current_stream(self.device).wait_stream(self.s_out)
 
     def __call__(self, host_inputs, sync=True):
         """Copy in, run, copy out, chunk by chunk; returns the tuple of pinned result tensors.  They are valid after
@@ -160,8 +103,6 @@ class HostPipeline(object):
         every call."""
         if self.host_out is None:
             self.host_out = self._alloc_host_out()
-        if self.fused:
-            return self._call_fused(host_inputs, sync)
         cur = torch.cuda.current_stream(self.device)
         if sync:
             self.s_in.wait_stream(cur)   # inputs produced by work queued on the caller's stream

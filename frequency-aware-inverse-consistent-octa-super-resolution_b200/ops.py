@@ -609,3 +609,16 @@ dwt2 = torch.ops.b200wave.dwt2
 idwt2 = torch.ops.b200wave.idwt2
 ssim_fwd = torch.ops.b200wave.ssim_fwd
 ssim_bwd = torch.ops.b200wave.ssim_bwd
+
+
+def ssim_bench_kernels(sets, win):
+    """The kernels one SSIM forward + backward step launches, for bench.py's per-kernel timing: yields
+    (name, fn(i), algorithmic bytes per pixel, FP32 FMA-class instructions per pixel).  ``sets`` = [(img1, img2), ...]."""
+    n = len(sets)
+    saved = [ssim_fwd(s[0].detach(), s[1], win, True, 3)[1] for s in sets]
+    gout = torch.ones((), device=sets[0][0].device)
+    return [
+        ("ssim_fwd", lambda i: ssim_fwd(sets[i % n][0].detach(), sets[i % n][1], win, True, 3), 4 * (2 + 3), 120),
+        ("ssim_bwd", lambda i: ssim_bwd(sets[i % n][0].detach(), sets[i % n][1], saved[i % n], gout, win, True, False),
+         4 * (5 + 1), 66),
+    ]

@@ -29,25 +29,41 @@ def shard_batch(x, rank=None, world_size=None):
     return x[lo:hi]
 
 
-def global_mean(local_mean, local_count, group=None):
-    """Mean over all ranks of per-rank means weighted by their element counts (ragged shards allowed).
-    Differentiable w.r.t. ``local_mean``: d global / d local_mean = local_count / total_count, which is
-    what sharding a ``size_average=True`` SSIM loss requires.  One all-reduce of 2 floats."""
+def global_mean(local_mean, local_count, group=None, reducer="mean", total_count=None):
+    """Mean over all ranks of per-rank means weighted by their element counts (ragged shards allowed).  One
+    all-reduce of 2 floats (1 when ``total_count`` is given, which also avoids the host read-back of the count).
+
+    The returned value is the global mean on every rank; its gradient flows through the local term only, scaled for
+    the gradient reducer that follows in the training step, so that the reduced parameter gradients equal those of the
+    single-process reference (``ssim_map.mean()`` over the whole batch, ``ssim.py:33-37``):
+
+    * ``reducer="mean"`` (default; torch DDP averages gradients over ranks):
+      d value / d local_mean = world_size * local_count / total_count   (1.0 for equal shards)
+    * ``reducer="sum"`` (gradients are summed over ranks): d value / d local_mean = local_count / total_count
+    """
+    if reducer not in ("mean", "sum"):
+        raise ValueError("reducer must be 'mean' or 'sum', not %r" % (reducer,))
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return local_mean
+    world = dist.get_world_size(group)
     with torch.no_grad():
-        buf = torch.stack([local_mean.detach().double() * float(local_count),
-                           torch.tensor(float(local_count), dtype=torch.float64, device=local_mean.device)])
-        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
-        total_sum, total_count = buf[0], buf[1]
-        value = (total_sum / total_count).to(local_mean.dtype)
-    # value carries the global number; the gradient flows through the local term only
-    weight = float(local_count) / float(total_count.item())
+        if total_count is None:
+            buf = torch.stack([local_mean.detach().double() * float(local_count),
+                               torch.tensor(float(local_count), dtype=torch.float64, device=local_mean.device)])
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+            total = float(buf[1].item())
+            total_sum = buf[0]
+        else:
+            total = float(total_count)
+            total_sum = local_mean.detach().double() * float(local_count)
+            dist.all_reduce(total_sum, op=dist.ReduceOp.SUM, group=group)
+        value = (total_sum / total).to(local_mean.dtype)
+    weight = float(local_count) / total * (world if reducer == "mean" else 1.0)
     return value.detach() + (local_mean - local_mean.detach()) * weight
 
 
-def sharded_ssim(ssim_module, img1, img2, group=None):
-    """``size_average=True`` SSIM over a batch that is sharded across ranks: each rank evaluates its
-    shard with the fused kernel, then the scalar means are combined."""
+def sharded_ssim(ssim_module, img1, img2, group=None, reducer="mean", total_count=None):
+    """``size_average=True`` SSIM over a batch that is sharded across ranks: each rank evaluates its shard with the
+    fused kernel, then the scalar means are combined (see ``global_mean`` for the gradient convention)."""
     local = ssim_module(img1, img2)
-    return global_mean(local, img1.numel(), group=group)
+    return global_mean(local, img1.numel(), group=group, reducer=reducer, total_count=total_count)

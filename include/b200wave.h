@@ -89,6 +89,9 @@ int b200w_last_cuda_error(void);
  * recent one ("" when out of range; the last 64 are kept).  bench.py counts its `gpu_launches` with these. */
 unsigned long long b200w_kernel_launches(void);
 const char* b200w_kernel_log(int back);
+/* hash of the sources (csrc/, include/) and compiler flags this binary was built from: the Python side compares it
+ * with the tree it runs in, so that numbers are never produced by kernels that do not match the committed sources */
+const char* b200w_build_hash(void);
 
 /* floor((n+l-1)/2), or ceil(n/2) for periodization; negative status for a bad mode */
 int b200w_dwt_coeff_len(int n, int l, int mode);

@@ -75,6 +75,75 @@ def _wave_taps(name):
     return w
 
 
+def guarded(a, grad=False, guard=4096):
+    """The array as a CUDA tensor that lives in the middle of a NaN-filled buffer: a kernel that reads before or
+    behind a tensor it was given picks up NaNs (the parity check then fails) instead of silently reading mapped
+    allocator memory.  compute-sanitizer is closed on this pool, so this is the in-tree substitute for global reads."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    buf = torch.full((a.size + 2 * guard,), float("nan"), dtype=torch.float32, device=DEV)
+    view = buf[guard:guard + a.size].view(a.shape)
+    view.copy_(torch.from_numpy(a))
+    view._guard_buf = buf
+    return view.requires_grad_(grad)
+
+
+def guards_intact(t):
+    buf = t._guard_buf
+    g = (buf.numel() - t.numel()) // 2
+    return bool(torch.isnan(buf[:g]).all() and torch.isnan(buf[g + t.numel():]).all())
+
+
+def roundtrip_vs_oracle(wave, J, mode, shape, seed=None):
+    """DWT, IDWT and the backward of both on seeded inputs against the numpy oracle; every tensor handed to the
+    library sits between NaN guard bands."""
+    rng = np.random.default_rng(hash((wave, J, mode)) % (2 ** 32) if seed is None else seed)
+    x = rng.standard_normal(shape).astype(np.float32)
+    xfm = b200wave.DWTForward(J=J, wave=wave, mode=mode).to(DEV)
+    ifm = b200wave.DWTInverse(wave=wave, mode=mode).to(DEV)
+    hc = (xfm.h0_col.flatten().cpu().numpy().astype(np.float64), xfm.h1_col.flatten().cpu().numpy().astype(np.float64))
+    gc = (ifm.g0_col.flatten().cpu().numpy().astype(np.float64), ifm.g1_col.flatten().cpu().numpy().astype(np.float64))
+    tx = guarded(x, grad=True)
+    yl, yh = xfm(tx)
+    oyl, oyh = dwt_oracle.dwt_forward(x.astype(np.float64), J, hc, hc, mode)
+    assert rel_err(yl.detach().cpu(), oyl) < RTOL_F32
+    for a, b in zip(yh, oyh):
+        assert rel_err(a.detach().cpu(), b) < RTOL_F32
+    rec = ifm((yl, yh))
+    orec = dwt_oracle.dwt_inverse(oyl, oyh, gc, gc, mode)
+    assert rel_err(rec.detach().cpu(), orec) < RTOL_F32
+    # the inverse once more on coefficients that sit between guard bands themselves
+    gl = guarded(yl.detach().cpu().numpy())
+    ghs = [guarded(t.detach().cpu().numpy()) for t in yh]
+    assert rel_err(ifm((gl, ghs)).cpu(), orec) < RTOL_F32
+    assert guards_intact(gl) and all(guards_intact(t) for t in ghs)
+    # full chain backward == oracle restatement of the reference's custom backwards
+    g = rng.standard_normal(orec.shape).astype(np.float32)
+    rec.backward(guarded(g))
+    assert guards_intact(tx)
+    # oracle: SFB2D.backward chain (finest first), then AFB2D.backward chain (coarsest first)
+    dy = g.astype(np.float64)
+    dhs = []
+    in_shapes = [x.shape[-2:]] + [h.shape[-2:] for h in oyh[:-1]]
+    for j in range(J):
+        dlow, dhigh = dwt_oracle.sfb2d_backward(dy, gc[0], gc[1], gc[0], gc[1], mode)
+        dhs.append(dhigh)
+        if j + 1 < J:
+            tgt = oyh[j + 1].shape[-2:]
+            L = len(gc[0])
+            full = tuple(2 * m if mode == "periodization" else 2 * m - L + 2 for m in tgt)
+            pad = np.zeros(dlow.shape[:2] + full)
+            pad[..., :dlow.shape[-2], :dlow.shape[-1]] = dlow
+            dy = pad
+    d = dlow
+    for j in reversed(range(J)):
+        d = dwt_oracle.afb2d_backward(d, dhs[j], hc[0], hc[1], hc[0], hc[1], mode, in_shapes[j])
+    assert rel_err(tx.grad.cpu(), d) < RTOL_F32
+    # perfect reconstruction (tests/test_dwt.py:64) where the sizes allow it
+    if all(s % (2 ** J) == 0 for s in shape[-2:]) or mode != "periodization":
+        r = rec.detach().cpu().numpy()[..., :shape[-2], :shape[-1]]
+        assert np.abs(r - x).max() < 2e-4 * max(1.0, np.abs(x).max())
+
+
 @pytest.mark.parametrize("wave,J,mode,shape", [
     ("haar", 3, "zero", (8, 1, 304, 304)),            # BASELINE cfg1
     ("db3", 3, "symmetric", (4, 1, 304, 304)),        # BASELINE cfg2 shape, smaller batch for the oracle
@@ -101,46 +170,26 @@ def _wave_taps(name):
     ("db7", 2, "periodization", (1, 1, 256, 132)),
 ])
 def test_oracle_dwt_roundtrip_seeded(wave, J, mode, shape):
-    rng = np.random.default_rng(hash((wave, J, mode)) % (2 ** 32))
-    x = rng.standard_normal(shape).astype(np.float32)
-    xfm = b200wave.DWTForward(J=J, wave=wave, mode=mode).to(DEV)
-    ifm = b200wave.DWTInverse(wave=wave, mode=mode).to(DEV)
-    hc = (xfm.h0_col.flatten().cpu().numpy().astype(np.float64), xfm.h1_col.flatten().cpu().numpy().astype(np.float64))
-    gc = (ifm.g0_col.flatten().cpu().numpy().astype(np.float64), ifm.g1_col.flatten().cpu().numpy().astype(np.float64))
-    tx = cu(x, grad=True)
-    yl, yh = xfm(tx)
-    oyl, oyh = dwt_oracle.dwt_forward(x.astype(np.float64), J, hc, hc, mode)
-    assert rel_err(yl.detach().cpu(), oyl) < RTOL_F32
-    for a, b in zip(yh, oyh):
-        assert rel_err(a.detach().cpu(), b) < RTOL_F32
-    rec = ifm((yl, yh))
-    orec = dwt_oracle.dwt_inverse(oyl, oyh, gc, gc, mode)
-    assert rel_err(rec.detach().cpu(), orec) < RTOL_F32
-    # full chain backward == oracle restatement of the reference's custom backwards
-    g = rng.standard_normal(orec.shape).astype(np.float32)
-    rec.backward(cu(g))
-    # oracle: SFB2D.backward chain (finest first), then AFB2D.backward chain (coarsest first)
-    dy = g.astype(np.float64)
-    dhs = []
-    in_shapes = [x.shape[-2:]] + [h.shape[-2:] for h in oyh[:-1]]
-    for j in range(J):
-        dlow, dhigh = dwt_oracle.sfb2d_backward(dy, gc[0], gc[1], gc[0], gc[1], mode)
-        dhs.append(dhigh)
-        if j + 1 < J:
-            tgt = oyh[j + 1].shape[-2:]
-            L = len(gc[0])
-            full = tuple(2 * m if mode == "periodization" else 2 * m - L + 2 for m in tgt)
-            pad = np.zeros(dlow.shape[:2] + full)
-            pad[..., :dlow.shape[-2], :dlow.shape[-1]] = dlow
-            dy = pad
-    d = dlow
-    for j in reversed(range(J)):
-        d = dwt_oracle.afb2d_backward(d, dhs[j], hc[0], hc[1], hc[0], hc[1], mode, in_shapes[j])
-    assert rel_err(tx.grad.cpu(), d) < RTOL_F32
-    # perfect reconstruction (tests/test_dwt.py:64) where the sizes allow it
-    if all(s % (2 ** J) == 0 for s in shape[-2:]) or mode != "periodization":
-        r = rec.detach().cpu().numpy()[..., :shape[-2], :shape[-1]]
-        assert np.abs(r - x).max() < 2e-4 * max(1.0, np.abs(x).max())
+    roundtrip_vs_oracle(wave, J, mode, shape)
+
+
+# Full-plane oracle parity at the sizes of the cfg5 sweep (BASELINE configs[4]): here different code runs than on the
+# small golden images -- many ring segments per row, the ticketed multi-level chain over big planes, sub-band widths
+# 513 .. 519 with 4-byte aligned rows, the shifting accumulator ring of the long filters at scale.
+_LARGE = [(size, wave, mode, J) for size in (1024, 2048) for wave in ("db1", "db4", "db8")
+          for mode in ("zero", "symmetric", "periodization") for J in (1, 5)]
+
+
+@pytest.mark.parametrize("size,wave,mode,J", _LARGE, ids=["%d-%s-%s-J%d" % c for c in _LARGE])
+def test_oracle_parity_large_planes(size, wave, mode, J):
+    roundtrip_vs_oracle(wave, J, mode, (2 if size == 1024 else 1, 1, size, size), seed=size + J)
+
+
+def test_oracle_parity_sweep_batch():
+    """One cfg5 point at its real batch geometry, cut to what the oracle finishes in seconds: 6 planes of 1024 x 1024
+    (more planes than one CTA wave leaves idle) and an odd-sized plane (1023 x 1025: unaligned rows, odd sub-bands)."""
+    roundtrip_vs_oracle("db3", 3, "symmetric", (6, 1, 1024, 1024), seed=7)
+    roundtrip_vs_oracle("db4", 4, "symmetric", (1, 2, 1023, 1025), seed=8)
 
 
 def test_full_size_properties_cfg2():
@@ -365,16 +414,16 @@ def test_host_pipeline_matches_direct_call():
     gh = torch.randn(10, 1, 76, 76).pin_memory()
     xd = xh.detach().to(DEV).requires_grad_(True)
     rec_ref, dx_ref = step(xd, gh.to(DEV))
-    for chunks, graph, fused in [(1, False, False), (3, False, False), (4, True, False), (4, True, True), (5, True, True)]:
-        pipe = b200wave.HostPipeline(step, (xh, gh), chunks=chunks, graph=graph, fused=fused)
-        for _ in range(2):   # second call exercises buffer reuse (and, fused, the cached graphs)
+    for chunks, graph in [(1, False), (3, False), (4, True), (5, True)]:
+        pipe = b200wave.HostPipeline(step, (xh, gh), chunks=chunks, graph=graph)
+        for _ in range(2):   # second call exercises buffer reuse
             rec, dx = pipe((xh, gh))
         assert rec.shape == rec_ref.shape and dx.shape == dx_ref.shape
         assert rel_err(rec, rec_ref.detach().cpu()) < 1e-6
         assert rel_err(dx, dx_ref.detach().cpu()) < 1e-6
 
 
-@pytest.mark.parametrize("env", ["B200W_FORCE_TILED=1", "B200W_PLANE=1", "B200W_FORCE_DIRECT=1", "B200W_OWNER=2",
+@pytest.mark.parametrize("env", ["B200W_FORCE_TILED=1", "B200W_FORCE_DIRECT=1", "B200W_OWNER=2",
                                  "B200W_OWNER=2 B200W_OWNER_J0=1", "B200W_OWNER=0"])
 def test_alternative_kernel_paths(env):
     """The same golden / oracle cases through the other implementations of the path (the env switches are read
@@ -390,6 +439,24 @@ def test_alternative_kernel_paths(env):
     res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-x",
                           "-m", "gpu", "-k", "golden_dwt or golden_idwt or oracle_dwt_roundtrip or commutativity or "
                           "owner_kernel",
+                          "-p", "no:cacheprovider"],
+                         cwd=root, env=child_env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                         timeout=1500)
+    assert res.returncode == 0, res.stdout[-3000:]
+
+
+@pytest.mark.parametrize("env", ["B200W_OWNER=0", "B200W_OWNER=2", "B200W_TMA=0", "B200W_FORCE_TILED=1"])
+def test_large_planes_other_policies(env):
+    """The large-plane oracle comparisons through the other kernel-selection policies (child pytest: the switches are
+    read once per process)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    child_env = dict(os.environ)
+    for kv in env.split():
+        k, v = kv.split("=")
+        child_env[k] = v
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-x",
+                          "-m", "gpu", "-k", "large_planes and not other_policies and not 2048-db8 or sweep_batch",
                           "-p", "no:cacheprovider"],
                          cwd=root, env=child_env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
                          timeout=1500)

@@ -36,15 +36,58 @@ def _worker(rank, world, port, n_batch, out_dir):
         assert la.shape[0] == hi - lo
         # stand-in for the fused kernel on this rank's shard
         local = torch.tensor(ssim_oracle.ssim(la.numpy(), lb.numpy()), requires_grad=True)
-        g = global_mean(local, la.numel())
+        g = global_mean(local, la.numel(), reducer="sum")
         g.backward()
         full = ssim_oracle.ssim(a, b)
         assert abs(float(g) - full) < 1e-12, (float(g), full)
-        # d global / d local mean = share of the elements held by this rank
+        # summed over ranks: d global / d local mean = share of the elements held by this rank
         assert abs(float(local.grad) - (hi - lo) / n_batch) < 1e-12
+        # DDP convention (gradients averaged over ranks), count known on the host: no read-back
+        local2 = torch.tensor(ssim_oracle.ssim(la.numpy(), lb.numpy()), requires_grad=True)
+        g2 = global_mean(local2, la.numel(), reducer="mean", total_count=ta.numel())
+        g2.backward()
+        assert abs(float(g2) - full) < 1e-12
+        assert abs(float(local2.grad) - world * (hi - lo) / n_batch) < 1e-12
         np.save(os.path.join(out_dir, "rank%d.npy" % rank), np.array([float(g)]))
     finally:
         dist.destroy_process_group()
+
+
+def _ddp_worker(rank, world, port, n_batch, out_dir):
+    """A shared parameter, a mean-type loss over a sharded batch, gradients averaged over ranks as DDP does: the
+    reduced gradient must equal the unsharded one -- also for ragged shards."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        gen = torch.Generator().manual_seed(3)
+        x = torch.rand((n_batch, 1, 6, 7), generator=gen, dtype=torch.float64)
+        w0 = torch.rand((1, 1, 6, 7), generator=gen, dtype=torch.float64)
+
+        def loss_of(w, batch):      # any per-pixel map followed by .mean(), like ssim_map.mean() (ssim.py:35)
+            return torch.sigmoid(w * batch).mean()
+
+        w_full = w0.clone().requires_grad_(True)
+        loss_of(w_full, x).backward()
+        w = w0.clone().requires_grad_(True)
+        xs = shard_batch(x)
+        total = global_mean(loss_of(w, xs), xs.numel(), reducer="mean", total_count=x.numel())
+        total.backward()
+        grad = w.grad.clone()
+        dist.all_reduce(grad, op=dist.ReduceOp.SUM)
+        grad /= world               # DDP's gradient averaging
+        assert torch.allclose(grad, w_full.grad, rtol=1e-12, atol=1e-15), (grad - w_full.grad).abs().max()
+        assert abs(float(total) - float(loss_of(w0, x))) < 1e-12
+        np.save(os.path.join(out_dir, "ddp%d.npy" % rank), np.array([1.0]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_batch", [4, 5])
+def test_sharded_mean_gradients_match_unsharded_under_ddp_averaging(tmp_path, n_batch):
+    port = _free_port()
+    mp.spawn(_ddp_worker, args=(2, port, n_batch, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ddp0.npy").exists() and (tmp_path / "ddp1.npy").exists()
 
 
 @pytest.mark.parametrize("n_batch", [4, 5])

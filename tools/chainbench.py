@@ -32,9 +32,11 @@ def case(n, h, w, wave, mode, J):
         ta = timeit(lambda i: xfm(xs[i % nsets]), nsets)
         ts = timeit(lambda i: ifm(cs[i % nsets]), nsets)
     by = pass_bytes(n, h, w, L, J, mode)
+    from b200wave import _cabi
+    ks = sorted(set(_cabi.recent_kernels(8)))
     print("%-5s %-13s J=%d %4dx%4dx%4d  DWT %7.1f us %5.0f GB/s (%4.1f%%)   IDWT %7.1f us %5.0f GB/s (%4.1f%%)" % (
         wave, mode, J, n, h, w, ta * 1e6, by / ta / 1e9, by / ta / 1e9 / PEAK * 100, ts * 1e6, by / ts / 1e9,
-        by / ts / 1e9 / PEAK * 100), flush=True)
+        by / ts / 1e9 / PEAK * 100), " ".join(k.replace("_kernel", "") for k in ks), flush=True)
 
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "cfg2":
