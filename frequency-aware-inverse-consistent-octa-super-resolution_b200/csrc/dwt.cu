@@ -1097,6 +1097,10 @@ static int run_sfb_chain(const float* yl, int64_t yl_ps, int64_t yl_rs, const fl
     }
     if (templated_taps(Lw, Lh)) {
         if (J > 1 && !force_tiled() && owner_mode() != 0) {
+            SfbTmaParams tp;
+            if (sfb_tma_plan(p, Lw, device_info().sms, owner_mode() == 2, tp)) return launch_sfb_tma(tp, Lw, st);
+        }
+        if (J > 1 && !force_tiled() && owner_mode() != 0) {
             SfbOwnerParams op;
             if (sfb_owner_plan(p, Lw, device_info().sms, owner_mode() == 2, op)) return launch_sfb_owner(op, Lw, st);
         }

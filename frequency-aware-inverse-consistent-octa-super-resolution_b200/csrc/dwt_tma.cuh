@@ -57,6 +57,44 @@ struct AfbTmaParams {
 };
 static_assert(sizeof(AfbTmaParams) <= 4096, "kernel parameter block");
 
+// ---- synthesis ---------------------------------------------------------------------------------------------------
+// Chain positions run coarsest first.  The detail rows a part needs are contiguous in global memory (dense
+// (planes, 3, h, w) tensors), so they come in as plain bulk copies (cp.async.bulk, one per band): the copy covers the
+// 16-byte aligned superset of the rows and the data sits 0..3 floats into the destination, rows dense at pitch w --
+// any width, any row alignment.  Every position but the last is "resident" (all its rows fetched at kernel start); the
+// last, finest position streams its rows through per-stream mbarrier rings.
+struct SfbTmaPos {
+    float* y;              // global output (last position only)
+    const float* highs;    // global (planes, 3, h, w)
+    int h, w, out_h, out_w;
+    int nq;                // lanes per segment = ceil(out_w / 4)
+    int Rp, nseg;          // output row pairs per segment, segments
+    int v2;                // detail rows are 8-byte aligned in shared memory (even w): 64-bit window loads
+    int res_off, res_band; // resident positions: byte offset of the detail rows, bytes reserved per band
+    int y_off, y_pitch, y_rows;   // output image in shared memory (all positions but the last): byte offset, pitch, rows
+    int vec4;              // 128-bit global stores allowed (last position)
+    int n0[kMaxParts], n1[kMaxParts];   // output rows [n0, n1) a part computes
+    int k0[kMaxParts], k1[kMaxParts];   // coefficient rows [k0, k1) it reads
+};
+
+struct SfbTmaParams {
+    SfbTmaPos pos[kMaxLevels];
+    TapsT t;
+    const float* yl;                  // dense (planes, h, w) low-pass input of the first position
+    int J, planes, parts;
+    int D, SR;                        // ring stages of the last position, coefficient rows per stage
+    int ring_band;                    // bytes reserved per band inside a ring stage
+    int low_off;                      // resident yl rows (first position)
+    int bar_off, ring_off;
+    int smem_bytes;
+    int dbg;
+    unsigned long long* timeline;
+};
+static_assert(sizeof(SfbTmaParams) <= 4096, "kernel parameter block");
+
+bool sfb_tma_plan(const SfbParams& p, int L, int sms, bool force, SfbTmaParams& tp);
+int launch_sfb_tma(const SfbTmaParams& tp, int L, cudaStream_t st);
+
 // planning + launch (dwt_tma_afb.cu).  afb_tma_plan returns false when the shapes do not qualify (unaligned rows, the
 // low-pass images do not fit, the driver has no tensor-map entry point, ...): the caller then takes the other kernels.
 bool afb_tma_plan(const AfbParams& p, int L, int sms, bool force, AfbTmaParams& tp);

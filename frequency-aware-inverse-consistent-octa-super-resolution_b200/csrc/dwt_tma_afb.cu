@@ -183,6 +183,7 @@ struct ConstTaps {   // long filters: the taps stay in the constant bank
 
 // where a lane's completed output rows go
 struct AfbtOut {
+    int dbg;
     unsigned ll_s;         // shared address of the low-pass pair in the next level's input image (row of `orow`)
     unsigned ll_pitch_b;   // its row pitch in bytes
     float* low;            // last level: global address of the low-pass pair (row of `orow`)
@@ -200,7 +201,7 @@ __device__ __forceinline__ void afbt_store(const float2* s, AfbtOut& o) {
     if ((unsigned)(o.orow - o.i0) < (unsigned)o.nout) {
         const bool g = (unsigned)(o.orow - o.hlo) < (unsigned)o.hn;
         if (!LAST) {
-            sts64t(o.ll_s, s[0]);
+            if (!(o.dbg & 32)) sts64t(o.ll_s, s[0]);
         } else if (g) {
             if (o.low_vec2) {
                 *reinterpret_cast<float2*>(o.low) = s[0];
@@ -209,7 +210,7 @@ __device__ __forceinline__ void afbt_store(const float2* s, AfbtOut& o) {
                 if (o.c1ok) o.low[1] = s[0].y;
             }
         }
-        if (g) {
+        if (g && !(o.dbg & 16)) {
             if (o.vec2) {
                 *reinterpret_cast<float2*>(o.hi) = s[1];
                 *reinterpret_cast<float2*>(o.hi + o.band) = s[2];
@@ -456,6 +457,7 @@ __global__ void __launch_bounds__(AfbT<L, OFF>::NT, 1) afb_tma_kernel(const __gr
             const unsigned bar_rel = bar_empty + 8u * (g * D);
             const AfbTmaLevel& l1 = p.lv[1];
             AfbtOut o;
+            o.dbg = p.dbg;
             o.orow = i0 - (H2 - 1);
             o.i0 = i0; o.nout = nout;
             o.hlo = max(i0, l0.h0[part]);
@@ -526,6 +528,7 @@ __global__ void __launch_bounds__(AfbT<L, OFF>::NT, 1) afb_tma_kernel(const __gr
         const int* const rt = tabs + lv.rtab_off + 2 * (i0 - c0);
         const unsigned lane_b = sbase + (unsigned)cp * 16u;   // + table entry = the window of this lane in that row
         AfbtOut o;
+        o.dbg = p.dbg;
         o.orow = i0 - (H2 - 1);
         o.i0 = i0; o.nout = nout;
         o.hlo = max(i0, lv.h0[part]);

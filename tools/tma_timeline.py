@@ -15,9 +15,9 @@ import b200wave  # noqa: E402
 n, h, w, wave, mode, J = 64, 304, 304, "db3", "symmetric", 3
 if len(sys.argv) > 6:
     n, h, w, wave, mode, J = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), sys.argv[4], sys.argv[5], int(sys.argv[6])
-path = os.environ.get("B200W_TMA_TIMELINE")
-assert path, "set B200W_TMA_TIMELINE"
 which = os.environ.get("TL_WHICH", "dwt")
+path = os.environ.get("B200W_TMA_TIMELINE" if which == "dwt" else "B200W_TMA_TIMELINE_SFB")
+assert path, "set B200W_TMA_TIMELINE (TL_WHICH=dwt) or B200W_TMA_TIMELINE_SFB (TL_WHICH=idwt)"
 xfm = b200wave.DWTForward(J=J, wave=wave, mode=mode).cuda()
 ifm = b200wave.DWTInverse(wave=wave, mode=mode).cuda()
 x = torch.rand(n, 1, h, w, device="cuda")
@@ -32,9 +32,12 @@ clk = 1.9   # GHz, close enough for phase shares
 g0 = t[:, 0] - t[:, 0].min()
 print("%s %dx%dx%d %s %s J=%d: %d CTAs; start spread (globaltimer) %.2f us" % (which, n, h, w, wave, mode, J, len(t), g0.max() / 1e3))
 names = ["set-up"]
-for j in range(1, J):
-    names += ["level/pos %d" % (j - 1), "patch %d" % j]
-names += ["level/pos %d" % (J - 1)]
+if which == "dwt":
+    for j in range(1, J):
+        names += ["level/pos %d" % (j - 1), "patch %d" % j]
+    names += ["level/pos %d" % (J - 1)]
+else:
+    names += ["(mark)"] + ["level/pos %d" % j for j in range(J)]
 prev = t[:, 1]
 for i, nm in enumerate(names):
     cur = t[:, 2 + i]
@@ -45,6 +48,8 @@ tot = (prev - t[:, 1]) / clk / 1e3
 print("  %-14s median %6.2f us  min %6.2f  max %6.2f" % ("total", np.median(tot), tot.min(), tot.max()))
 
 ref = t[:, 2]
+if which != "dwt":
+    sys.exit(0)
 for lbl, base in (("stream 0: stage landed (service warp)", 8), ("stream 0: stage patched + released", 24), ("stream 0: consumers start stage", 16), ("stream 0: prologue issue k done", 48),
                   ("stream 0: stage k free again (service warp)", 32), ("stream 0: stage k+D issued", 40)):
     vals = []
