@@ -15,6 +15,7 @@ namespace b200w {
 
 constexpr int kTmaMaxStreams = 8;    // row streams (segments of the streamed level) per CTA
 constexpr int kTmaMaxStrips = 4;     // tiles per staged row (a tile is at most 256 floats wide)
+constexpr int kAfbTabMax = 5120;     // ints of host-built tables in the analysis kernel's parameter block
 
 // taps of the templated kernels (<= 16), W taps as constant-bank scalars, H taps once more as (t, t) pairs for FFMA2
 struct TapsT {
@@ -47,6 +48,8 @@ struct AfbTmaParams {
     TapsT t;
     int J, planes, parts, mode;
     int D, nstrips, cps, BW;   // ring: stages, tiles per row, column pairs per tile, tile width (floats, multiple of 32)
+    int boxes;                 // 1: every ring stage is one box of consecutive (virtual) rows (see the kernel)
+    int rp0_off, rp0_stride;   // per-pair row-address table of the first level: int offset, int2 entries per stream
     int fix0_off, fix0_n;      // int offset of the ring's column-patch table (int2 per stage row x extension column) and
                                // the extension columns per stage row
     int dbg;                   // debug (B200W_TMA_DBG): 1 = consumers do not wait for the data, 2 = consumers skip the arithmetic
@@ -54,8 +57,11 @@ struct AfbTmaParams {
     int bar_off, tab_off, zrow_off, ring_off;   // shared-memory layout (bytes from the dynamic base)
     int zrow_floats, tab_ints;
     int smem_bytes;
+    // the row / patch tables of every part, built on the host (part q's tab_ints entries start at q * tab_ints): a CTA
+    // only copies its part's share into shared memory instead of spending ~2 us of set-up on index arithmetic
+    int tab[kAfbTabMax];
 };
-static_assert(sizeof(AfbTmaParams) <= 4096, "kernel parameter block");
+static_assert(sizeof(AfbTmaParams) <= 32764, "kernel parameter block (CUDA 12.1+: 32764 bytes)");
 
 // ---- synthesis ---------------------------------------------------------------------------------------------------
 // Chain positions run coarsest first.  The detail rows a part needs are contiguous in global memory (dense

@@ -42,7 +42,9 @@ struct AfbT {
     static constexpr int NV = (S + L + 2 + 3) / 4;   // float4 per window (two adjacent output columns)
     static constexpr int NE = 4 * NV;
     static constexpr bool kRotate = L >= 10;         // accumulator ring shifted instead of statically renamed
-    static constexpr int PS = kRotate ? 4 : (H2 == 3 ? 3 : 4);   // input row pairs per ring stage (multiple of L/2)
+    // input row pairs per ring stage (a multiple of L/2): long stages, because every stage costs its service warp a
+    // fixed ~1 us of issue + patch work on a sub-partition that is busy with consumer warps
+    static constexpr int PS = kRotate ? 4 : (H2 == 1 ? 4 : (H2 == 4 ? 8 : 6));   // 2 * PS >= 2 * (L - 2): mirrored rows lie in the same stage
     static constexpr int SR = 2 * PS;                // rows per stage
     static constexpr int NTC = L <= 6 ? 416 : (L <= 8 ? 352 : 256);   // consumer threads
     static constexpr int MAXG = L <= 8 ? 5 : 4;      // row streams of the first level = service warps
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(AfbT<L, OFF>::NT, 1) afb_tma_kernel(const __gr
     TMA_MARK(1);
     // every 64-byte line of the parameter block is touched by a different thread first: the constant-cache misses of a
     // freshly scheduled CTA then overlap instead of queueing up behind each other in the set-up code below
-    if (tid < (int)(sizeof(AfbTmaParams) / 64)) {
+    if (tid < (int)((sizeof(AfbTmaParams) - sizeof(int) * kAfbTabMax) / 64)) {
         const int v = reinterpret_cast<const int*>(&p)[tid * 16];
         asm volatile("" ::"r"(v));
     }
@@ -276,63 +278,12 @@ __global__ void __launch_bounds__(AfbT<L, OFF>::NT, 1) afb_tma_kernel(const __gr
     const int G = l0.nseg;
     const unsigned bar_full = sbase + p.bar_off, bar_ready = bar_full + 8u * G * D, bar_empty = bar_ready + 8u * G * D;
 
-    // ---- set-up: row tables, column-patch tables, barriers, the zero row (parameter block -> shared memory only) ----
-#pragma unroll 1
-    for (int j = 0; j < p.J; ++j) {
-        const AfbTmaLevel& lv = p.lv[j];
-        const int c0 = lv.c0[part];
-        const int nr = 2 * (lv.c1[part] - c0) + L;
-        int* const rt = tabs + lv.rtab_off;
-        for (int e = tid; e < nr; e += NT) {
-            const int m = afbt_map(2 * c0 - off + e, lv.H, lv.Hreal, mode);
-            int val = m;
-            if (j > 0) val = m < 0 ? p.zrow_off : lv.in_off + (m - p.lv[j - 1].c0[part]) * lv.in_pitch * 4;
-            rt[e] = val;
-        }
-        if (j > 0) {   // patch table of the input image: every float of a row that is not image data
-            int* const cf = tabs + lv.cfix_off;
-            const int n = lv.in_pitch - lv.Wreal;
-            for (int k = tid; k < n; k += NT) {
-                const int f = k < hl ? k : lv.Wreal + k;      // float index inside the row (column f - hl)
-                const int m = afbt_map(f - hl, lv.W, lv.Wreal, mode);
-                cf[2 * k] = f;
-                cf[2 * k + 1] = m < 0 ? -1 : m + hl;
-            }
-        }
+    // ---- set-up: this part's row / patch tables (built by the host, in the parameter block), barriers, the zero row ----
+    {
+        const int* const src = p.tab + part * p.tab_ints;
+        for (int i = tid; i < p.tab_ints; i += NT) tabs[i] = src[i];
     }
-    int nfix0 = 0;
-    {   // ring patch table: extension columns inside the tiles of a stage, one entry per (row of the stage, column):
-        // (destination, source) byte offsets from the stage base; source -1 = leave the engine's zero
-        int* const cf = tabs + p.fix0_off;
-        int base = 0;
-#pragma unroll 1
-        for (int s = 0; s < nstrips; ++s) {
-            const int b = 4 * s * cps - hl;                               // image column of the tile's first float
-            const int pairs = min(cps, l0.ncp - s * cps);
-            const int fmax = 4 * (pairs - 1) + NE - 1;                    // last float a lane of this tile reads
-            const int nl = s == 0 ? hl : 0;                               // left extension (first tile only)
-            const int fr = max(nl, l0.Wreal - b);                         // first float right of the data
-            const int n = nl + max(0, fmax + 1 - fr);
-            if (mode != B200W_MODE_ZERO) {
-                for (int ki = tid; ki < n * SR; ki += NT) {
-                    const int k = ki / SR, i = ki - k * SR;
-                    const int f = k < nl ? k : fr + (k - nl);
-                    const int m = afbt_map(b + f, l0.W, l0.Wreal, mode);
-                    int src = -1;
-                    if (m >= 0) {   // the tile that holds column m: this one if it does, else the one its pair lives in
-                        int s2 = s;
-                        if (m < b || m >= b + BW) s2 = min(nstrips - 1, max(0, (m + hl) / (4 * cps)));
-                        src = s2 * (int)srbw4 + (m - (4 * s2 * cps - hl)) * 4;
-                    }
-                    const int dst = s * (int)srbw4 + f * 4;
-                    cf[2 * (i * p.fix0_n + base + k)] = dst + i * BW * 4;
-                    cf[2 * (i * p.fix0_n + base + k) + 1] = src < 0 ? -1 : src + i * BW * 4;
-                }
-                base += n;
-            }
-        }
-        nfix0 = base;
-    }
+    const int nfix0 = mode != B200W_MODE_ZERO ? p.fix0_n : 0;
     for (int i = tid; i < p.zrow_floats; i += NT) reinterpret_cast<float*>(smem + p.zrow_off)[i] = 0.f;
     if (tid < G * D) {
         mbar_init(bar_full + 8u * tid, 1);
@@ -367,36 +318,35 @@ __global__ void __launch_bounds__(AfbT<L, OFF>::NT, 1) afb_tma_kernel(const __gr
             const int npairs = min(l0.R, c1_0 - i0) + H2 - 1;
             const int nst = (npairs + PS - 1) / PS;
             const int e0 = 2 * (i0 - c0_0);
+            const int r_start = 2 * i0 - off;                            // first (virtual) input row of the stream
             const unsigned ring = sbase + p.ring_off + (unsigned)(g * D) * stage_b;
             const int* const cf = tabs + p.fix0_off;
             const int npatch = SR * nfix0;
+            // p.boxes: every stage is ONE box of consecutive (virtual) rows; rows above / below the image arrive
+            // zero-filled, and where the padding mode maps them onto image rows (symmetric, reflect) the consumers'
+            // row table points at those rows instead.  Otherwise (wrapping modes) such stages are fetched row by row
+            // from their source rows.
+            const bool boxes = p.boxes != 0;
+#define SVC_MARK(slot, k) do { if (p.timeline && g == 0 && lane == 0 && (k) < 8) p.timeline[(size_t)blockIdx.x * 64 + (slot) + (k)] = (unsigned long long)clock64(); } while (0)
             auto issue = [&](int k) {
                 const int st = k % D;
                 const unsigned full = bar_full + 8u * (g * D + st);
-#define ISS_MARK(i) do { if (p.timeline && g == 0 && k == 1) p.timeline[(size_t)blockIdx.x * 64 + 56 + (i)] = (unsigned long long)clock64(); } while (0)
-                ISS_MARK(0);
-                if (!(p.dbg & 4)) fence_proxy_async();
-                ISS_MARK(1);
                 const unsigned dst = ring + (unsigned)st * stage_b;
+                if (boxes) {   // rows outside the tensor are zero-filled by the copy engine
+                    mbar_expect_tx(full, stage_b);
+                    for (int t = 0; t < nstrips; ++t)
+                        tma_load_3d(dst + (unsigned)t * srbw4, &p.map_full, full, 4 * t * cps - hl, r_start + k * SR, plane);
+                    return;
+                }
                 const int eb = e0 + k * SR;
                 const int need = min(SR, 2 * npairs - k * SR);          // rows of this stage somebody reads
-                bool regular;
-                int rfirst;
-                if (mode == B200W_MODE_ZERO) {   // rows outside the tensor are zero-filled by the copy engine
-                    regular = true;
-                    rfirst = 2 * i0 - off + k * SR;
-                } else {
-                    rfirst = rt0[eb];
-                    regular = rfirst >= 0;
-                    for (int i = 1; i < need; ++i) regular = regular && rt0[eb + i] == rfirst + i;
-                }
-                ISS_MARK(2);
+                int rfirst = rt0[eb];
+                bool regular = rfirst >= 0;
+                for (int i = 1; i < need; ++i) regular = regular && rt0[eb + i] == rfirst + i;
                 if (regular) {
                     mbar_expect_tx(full, stage_b);
-                    ISS_MARK(3);
                     for (int t = 0; t < nstrips; ++t)
                         tma_load_3d(dst + (unsigned)t * srbw4, &p.map_full, full, 4 * t * cps - hl, rfirst, plane);
-                    ISS_MARK(4);
                 } else {
                     mbar_expect_tx(full, (unsigned)(need * nstrips * BW * 4));
                     for (int i = 0; i < need; ++i) {
@@ -410,33 +360,37 @@ __global__ void __launch_bounds__(AfbT<L, OFF>::NT, 1) afb_tma_kernel(const __gr
             };
             auto patch = [&](int k) {
                 const int st = k % D;
+                if (k == 0) SVC_MARK(8, 0);
                 mbar_wait(bar_full + 8u * (g * D + st), (unsigned)((k / D) & 1));
-                if (p.timeline && g == 0 && lane == 0 && k < 8) p.timeline[(size_t)blockIdx.x * 64 + 8 + k] = (unsigned long long)clock64();
+                if (k == 0) SVC_MARK(8, 1);
                 const unsigned base = ring + (unsigned)st * stage_b;
+                if (k == 0) SVC_MARK(8, 2);
 #pragma unroll 2
                 for (int it = lane; it < npatch; it += 32) {
                     const int2 ds = *reinterpret_cast<const int2*>(cf + 2 * it);
                     if (ds.y >= 0) sts32t(base + (unsigned)ds.x, lds32t(base + (unsigned)ds.y));
                 }
                 mbar_arrive(bar_ready + 8u * (g * D + st));
-                if (p.timeline && g == 0 && lane == 0 && k < 8) p.timeline[(size_t)blockIdx.x * 64 + 24 + k] = (unsigned long long)clock64();
+                if (k == 0) SVC_MARK(8, 3);
             };
+            // the first two stages go out first, so that the consumers can start while the rest of the ring is filled
+            SVC_MARK(48, 0);
             if (lane == 0)
-                for (int k = 0; k < min(D, nst); ++k) {
-                    issue(k);
-                    if (p.timeline && g == 0 && k < 8) p.timeline[(size_t)blockIdx.x * 64 + 48 + k] = (unsigned long long)clock64();
-                }
+                for (int k = 0; k < min(2, nst); ++k) { issue(k); SVC_MARK(48, 1 + k); }
             __syncwarp();
-            if (use_ready) patch(0);
+            if (use_ready) { patch(0); SVC_MARK(24, 0); }
+            if (lane == 0)
+                for (int k = 2; k < min(D, nst); ++k) issue(k);
+            __syncwarp();
 #pragma unroll 1
             for (int k = 0; k < nst; ++k) {
-                if (use_ready && k + 1 < nst) patch(k + 1);
+                if (use_ready && k + 1 < nst) { patch(k + 1); SVC_MARK(24, k + 1); }
                 if (k + D < nst) {
                     mbar_wait(bar_empty + 8u * (g * D + k % D), (unsigned)((k / D) & 1));
-                    if (p.timeline && g == 0 && lane == 0 && k < 8) p.timeline[(size_t)blockIdx.x * 64 + 32 + k] = (unsigned long long)clock64();
+                    SVC_MARK(32, k);
                     if (lane == 0) issue(k + D);
                     __syncwarp();
-                    if (p.timeline && g == 0 && lane == 0 && k < 8) p.timeline[(size_t)blockIdx.x * 64 + 40 + k] = (unsigned long long)clock64();
+                    SVC_MARK(40, k);
                 }
             }
         }
@@ -451,8 +405,10 @@ __global__ void __launch_bounds__(AfbT<L, OFF>::NT, 1) afb_tma_kernel(const __gr
             const int npairs = nout + H2 - 1;
             const int nst = (npairs + PS - 1) / PS;
             const int s = cp / cps, cl = cp - s * cps;
-            const unsigned lane_ring = sbase + p.ring_off + (unsigned)(g * D) * stage_b + (unsigned)s * srbw4 + (unsigned)cl * 16u;
-            const unsigned pitch_b = (unsigned)BW * 4u;
+            // rows come through a per-pair table of shared-memory row addresses (built by the host): a row above /
+            // below the image that the padding mode maps onto an image row is simply read from that row's ring slot
+            const unsigned lane_ring = sbase + (unsigned)s * srbw4 + (unsigned)cl * 16u;
+            const int2* const rp = reinterpret_cast<const int2*>(tabs + p.rp0_off) + g * p.rp0_stride;
             const unsigned bar_wait = (use_ready ? bar_ready : bar_full) + 8u * (g * D);
             const unsigned bar_rel = bar_empty + 8u * (g * D);
             const AfbTmaLevel& l1 = p.lv[1];
@@ -477,16 +433,16 @@ __global__ void __launch_bounds__(AfbT<L, OFF>::NT, 1) afb_tma_kernel(const __gr
 #pragma unroll 1
             for (int k = 0; k < nst; ++k) {
                 if (!(p.dbg & 1)) mbar_wait(bar_wait + 8u * st, ph);
-                unsigned a = lane_ring + (unsigned)st * stage_b;
+                if (p.timeline && tid == 0 && k < 8) p.timeline[(size_t)blockIdx.x * 64 + 16 + k] = (unsigned long long)clock64();
                 if (!(p.dbg & 2))
 #pragma unroll
                 for (int u = 0; u < PS; ++u) {
+                    const int2 ro = rp[k * PS + u];
                     float v[2][NE];
-                    afbt_load<L, OFF>(v, a, a + pitch_b);
+                    afbt_load<L, OFF>(v, lane_ring + (unsigned)ro.x, lane_ring + (unsigned)ro.y);
                     afbt_pair<L, OFF>(taps, v, acc, u % H2);
                     afbt_store<L, OFF, false>(acc[kRotate ? 0 : (u + 1) % H2], o);
                     afbt_rotate<L, OFF>(acc);
-                    a += 2u * pitch_b;
                 }
                 if (!(p.dbg & 8)) mbar_arrive(bar_rel + 8u * st);
                 if (++st == D) { st = 0; ph ^= 1u; }
@@ -664,9 +620,17 @@ static bool afb_tma_plan_t(const AfbParams& p, int sms, bool force, AfbTmaParams
     // segments: level 0 = the row streams (each needs ring stages and barriers), later levels as many as lanes allow
     {
         AfbTmaLevel& lv = t.lv[0];
-        int G = std::min(C::MAXG, std::max(1, NTC / lv.ncp));
-        if (const char* e = getenv("B200W_TMA_G")) G = std::max(1, std::min(G, atoi(e)));
-        G = std::min(std::min(G, 32), maxrows[0]);
+        // streams: the busiest SM sub-partition bounds the level (the march is FP32-pipe bound): it runs
+        // ceil(warps / 4) warps for R + L/2 - 1 row pairs each -- fewer, longer streams often beat filling every lane
+        const int gmax = std::min(std::min(C::MAXG, std::max(1, NTC / lv.ncp)), std::min(32, maxrows[0]));
+        int G = 1;
+        long long best = -1;
+        for (int g = 1; g <= gmax; ++g) {
+            const int warps = ceil_div(g * lv.ncp, 32);
+            const long long cost = (long long)ceil_div(warps, 4) * (ceil_div(maxrows[0], g) + C::H2 - 1);
+            if (best < 0 || cost < best) { best = cost; G = g; }
+        }
+        if (const char* e = getenv("B200W_TMA_G")) G = std::max(1, std::min(gmax, atoi(e)));
         lv.R = ceil_div(maxrows[0], G);
         lv.nseg = ceil_div(maxrows[0], lv.R);
     }
@@ -722,6 +686,10 @@ static bool afb_tma_plan_t(const AfbParams& p, int sms, bool force, AfbTmaParams
         t.fix0_n = n;
         ti += 2 * n * SR;
     }
+    // per-pair row tables of the first level: G streams x (R + L/2 - 1 rounded up to whole stages) x int2
+    t.rp0_stride = ceil_div(t.lv[0].R + C::H2 - 1, C::PS) * C::PS;
+    t.rp0_off = ti;
+    ti += 2 * t.rp0_stride * t.lv[0].nseg;
     t.tab_ints = ti;
     t.tab_off = (int)o;
     o += (size_t)ti * 4;
@@ -748,6 +716,108 @@ static bool afb_tma_plan_t(const AfbParams& p, int sms, bool force, AfbTmaParams
     if (D < 2) return false;
     t.D = D;
     t.smem_bytes = (int)(o + std::max(later, (size_t)D * stage_b * t.lv[0].nseg));
+    // the tables, per part (the same layout the kernel indexes: row tables, column-patch tables, ring patch table)
+    if ((long long)t.tab_ints * parts > kAfbTabMax) return false;
+    {
+        auto map = [&](int sidx, int n, int real) {
+            if (sidx >= 0 && sidx < real) return sidx;
+            if (sidx >= 0 && sidx < n) return -1;                 // zero extension inside the logical size
+            if (p.mode == B200W_MODE_ZERO) return -1;
+            const int m = ext_index(sidx, n, p.mode);
+            return (m < 0 || m >= real) ? -1 : m;
+        };
+        const int srbw4 = SR * t.BW * 4;
+        const int stage_bytes = t.nstrips * srbw4;
+        // Can every stage be one box of consecutive virtual rows?  Yes for 'zero'; for symmetric / reflect when every
+        // extension row finds its image row in a ring slot that is still valid when it is read: the same stage, or an
+        // earlier stage of the stream that is never refilled (one of the last D stages).
+        bool boxes = p.mode == B200W_MODE_ZERO || p.mode == B200W_MODE_SYMMETRIC || p.mode == B200W_MODE_REFLECT;
+        if (getenv("B200W_TMA_NOBOXES") && p.mode != B200W_MODE_ZERO) boxes = false;
+        for (int pass = 0; pass < 2; ++pass) {   // pass 0: decide `boxes`; pass 1: fill the tables
+        for (int q = 0; q < parts; ++q) {
+            int* const tb = t.tab + q * t.tab_ints;
+            const AfbTmaLevel& lz = t.lv[0];
+            for (int g = 0; g * lz.R < lz.c1[q] - lz.c0[q]; ++g) {
+                const int i0 = lz.c0[q] + g * lz.R;
+                const int npairs = std::min(lz.R, lz.c1[q] - i0) + C::H2 - 1;
+                const int nst = ceil_div(npairs, C::PS);
+                const int r_start = 2 * i0 - off;
+                for (int qq = 0; qq < t.rp0_stride; ++qq)
+                    for (int e = 0; e < 2; ++e) {
+                        const int v = r_start + 2 * qq + e;          // virtual input row of this pair
+                        int rowv = v;                                 // the (virtual) row whose ring slot is read
+                        if (boxes && qq < npairs && !(v >= 0 && v < lz.H)) {
+                            const int m = map(v, lz.H, lz.Hreal);
+                            if (m >= 0) {
+                                const int ks = m >= r_start ? (m - r_start) / SR : -1, k = (v - r_start) / SR;
+                                if (ks < 0 || ks >= nst || ks > k || (ks < k && ks + t.D < nst)) boxes = false;
+                                rowv = m;
+                            }
+                        }
+                        if (pass == 1) {
+                            const int kk = (rowv - r_start) / SR, ii = (rowv - r_start) - kk * SR;
+                            tb[t.rp0_off + 2 * (g * t.rp0_stride + qq) + e] =
+                                t.ring_off + (g * t.D + kk % t.D) * stage_bytes + ii * t.BW * 4;
+                        }
+                    }
+            }
+            if (pass == 0) continue;
+            for (int i = 0; i < t.rp0_off; ++i) tb[i] = 0;
+            for (int j = 0; j < J; ++j) {
+                const AfbTmaLevel& lv = t.lv[j];
+                const int c0 = lv.c0[q];
+                const int nr = 2 * (lv.c1[q] - c0) + L;
+                for (int e = 0; e < nr; ++e) {
+                    const int m = map(2 * c0 - off + e, lv.H, lv.Hreal);
+                    int val = m;
+                    if (j > 0) val = m < 0 ? t.zrow_off : lv.in_off + (m - t.lv[j - 1].c0[q]) * lv.in_pitch * 4;
+                    tb[lv.rtab_off + e] = val;
+                }
+                if (j > 0) {   // patch table of the input image: every float of a row that is not image data
+                    const int n = lv.in_pitch - lv.Wreal;
+                    for (int k = 0; k < n; ++k) {
+                        const int f = k < hl ? k : lv.Wreal + k;      // float index inside the row (column f - hl)
+                        const int m = map(f - hl, lv.W, lv.Wreal);
+                        tb[lv.cfix_off + 2 * k] = f;
+                        tb[lv.cfix_off + 2 * k + 1] = m < 0 ? -1 : m + hl;
+                    }
+                }
+            }
+            // ring patch table: extension columns inside the tiles of a stage, one entry per (row of the stage,
+            // column): (destination, source) byte offsets from the stage base; source -1 = leave the engine's zero
+            const AfbTmaLevel& l0t = t.lv[0];
+            int base = 0;
+            for (int s = 0; s < t.nstrips && p.mode != B200W_MODE_ZERO; ++s) {
+                const int b = 4 * s * t.cps - hl;                          // image column of the tile's first float
+                const int pairs = std::min(t.cps, l0t.ncp - s * t.cps);
+                const int fmax = 4 * (pairs - 1) + NE - 1;                 // last float a lane of this tile reads
+                const int nl = s == 0 ? hl : 0;                            // left extension (first tile only)
+                const int fr = std::max(nl, l0t.Wreal - b);                // first float right of the data
+                const int n = nl + std::max(0, fmax + 1 - fr);
+                for (int k = 0; k < n; ++k) {
+                    const int f = k < nl ? k : fr + (k - nl);
+                    const int m = map(b + f, l0t.W, l0t.Wreal);
+                    int src = -1;
+                    if (m >= 0) {   // the tile that holds column m: this one if it does, else the one its pair lives in
+                        int s2 = s;
+                        if (m < b || m >= b + t.BW) s2 = std::min(t.nstrips - 1, std::max(0, (m + hl) / (4 * t.cps)));
+                        src = s2 * srbw4 + (m - (4 * s2 * t.cps - hl)) * 4;
+                    }
+                    const int dst = s * srbw4 + f * 4;
+                    for (int i = 0; i < SR; ++i) {
+                        tb[t.fix0_off + 2 * (i * t.fix0_n + base + k)] = dst + i * t.BW * 4;
+                        tb[t.fix0_off + 2 * (i * t.fix0_n + base + k) + 1] = src < 0 ? -1 : src + i * t.BW * 4;
+                    }
+                }
+                base += n;
+            }
+        }
+        if (pass == 0 && !boxes) {   // the tables are rebuilt with every pair reading its own virtual rows
+            // (nothing to undo: pass 0 wrote nothing)
+        }
+        }
+        t.boxes = boxes ? 1 : 0;
+    }
     // tensor maps of the level-0 input
     const uint64_t dims[3] = {(uint64_t)x0.Wreal, (uint64_t)x0.Hreal, (uint64_t)p.planes};
     const uint64_t strides[2] = {(uint64_t)x0.x_rs * 4, (uint64_t)x0.x_ps * 4};

@@ -245,9 +245,10 @@ __global__ void __launch_bounds__(SfbT<L>::NT, 1) sfb_tma_kernel(const __grid_co
     __syncthreads();
     SFB_MARK(2);
 
-    // ---- resident positions: one bulk copy per band (and one for yl), issued by the first lanes of warp 0 ----
-    if (warp == 0) {
-        for (int c = 0; c + 1 < J; ++c) {
+    // ---- resident positions: one bulk copy per band (and one for yl); position c is issued by warp c ----
+    if (warp < J - 1) {
+        {
+            const int c = warp;
             const SfbTmaPos& ps = p.pos[c];
             const int k0 = ps.k0[part], rows = ps.k1[part] - k0;
             const size_t band = (size_t)ps.h * ps.w;
@@ -313,25 +314,34 @@ __global__ void __launch_bounds__(SfbT<L>::NT, 1) sfb_tma_kernel(const __grid_co
     }
 
     // ---- all chain positions, coarsest first ----
+    // The consumer code below runs in warp-uniform control flow (role and trip counts are broadcast values, lanes
+    // without work only skip their barrier operations and stores), so that the compiler may keep the taps and the
+    // loop state in uniform registers: inside a divergent region every tap would be a register operand of its own.
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
 #pragma unroll 1
     for (int c = 0; c < J; ++c) {
         const SfbTmaPos& ps = p.pos[c];
         const bool last = c + 1 == J;
-        if (warp >= kServiceWarp) break;   // the service warps feed the last position's ring meanwhile: they must not be
-                                           // waited for between positions
+        if (warp_u >= kServiceWarp) break;   // the service warps feed the last position's ring meanwhile: they must not be
+                                             // waited for between positions
         // the previous position's output image is complete: barrier among the consumer warps only
         if (c > 0) asm volatile("bar.sync 1, %0;" ::"r"(NTC) : "memory");
         SFB_MARK(2 + c + 1);
         const int n0 = ps.n0[part], n1 = ps.n1[part];
         const int m_lo = (n0 + off) >> 1, m_hi = ((n1 - 1 + off) >> 1) + 1;
         const int ct = tid;
-        const int g = ct / ps.nq;
-        const int t = ct - g * ps.nq;
-        const int m0 = m_lo + g * ps.Rp;
-        if (m0 >= m_hi) continue;
-        if (last && g >= nsegL) continue;
+        int g = ct / ps.nq;
+        int t = ct - g * ps.nq;
+        int m0 = m_lo + g * ps.Rp;
+        const bool has_work = m0 < m_hi && !(last && g >= nsegL);
+        if (!has_work) { g = 0; t = 0; m0 = m_lo; }           // a lane without work shadows lane 0's addresses
         const int nm = min(ps.Rp, m_hi - m0);
-        const int nrows = nm + H2 - 1;
+        const int nrows = has_work ? nm + H2 - 1 : 0;
+        int nrows_u = nrows;                                   // the warp's trip count: the longest lane's
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) nrows_u = max(nrows_u, __shfl_xor_sync(0xffffffffu, nrows_u, o2));
+        nrows_u = __shfl_sync(0xffffffffu, nrows_u, 0);
+        if (nrows_u == 0) continue;
         const int kr0 = m0 - (H2 - 1);
         const int k0 = ps.k0[part];
         const size_t band = (size_t)ps.h * ps.w;
@@ -349,14 +359,14 @@ __global__ void __launch_bounds__(SfbT<L>::NT, 1) sfb_tma_kernel(const __grid_co
         }
         SfbtOut o;
         o.nrow = 2 * m0 - off;
-        o.row_lo = n0; o.row_hi = n1;
+        o.row_lo = n0; o.row_hi = has_work ? n1 : n0;          // no work: nothing is stored
         o.ncol = min(4, ps.out_w - 4 * t);
         o.vec4 = ps.vec4 != 0;
         o.y_pitch_b = (unsigned)ps.y_pitch * 4u;
         o.y_s = sbase + ps.y_off + (unsigned)((o.nrow - n0) * ps.y_pitch + 4 * t) * 4u;   // wraps for the rows before n0 (never stored)
         o.y_rs = ps.out_w;
         o.y = last ? ps.y + (size_t)plane * ps.out_h * ps.out_w + (long long)o.nrow * ps.out_w + 4 * t : nullptr;
-        typename std::conditional<C::kRegTaps, SfbRegTaps<L>, SfbConstTaps>::type taps(p.t, lds32s(sbase + p.bar_off + 8u * (J - 1 + 2 * G * D)));
+        const SfbConstTaps taps(p.t, 0.f);
         float2 acc[H2][4];
         constexpr int UQ = kRotate ? 1 : H2;
         // shift of band b's data inside its copy destination: (first copied element) & 3
@@ -371,10 +381,10 @@ __global__ void __launch_bounds__(SfbT<L>::NT, 1) sfb_tma_kernel(const __grid_co
                         (unsigned)(((eb + b * es + k0 * ps.w) & 3) + (kr0 - k0) * ps.w + 2 * t) * 4u;
             auto run = [&](auto vl, auto vh) {
 #pragma unroll 1
-                for (int qb = 0; qb < nrows; qb += UQ) {
+                for (int qb = 0; qb < nrows_u; qb += UQ) {
 #pragma unroll
                     for (int u = 0; u < UQ; ++u) {
-                        if (qb + u < nrows) {
+                        if (qb + u < nrows_u) {
                             sfbt_row<L, decltype(vl)::value, decltype(vh)::value>(taps, a_low, aH[0], aH[1], aH[2], acc, u);
                             if (qb + u >= H2 - 1) sfbt_store<false>(acc[kRotate ? 0 : (u + 1) % H2], o);
                             sfbt_rotate<L>(acc);
@@ -398,15 +408,18 @@ __global__ void __launch_bounds__(SfbT<L>::NT, 1) sfb_tma_kernel(const __grid_co
                 int r0 = kr0;                             // first coefficient row of the current stage
                 int st = 0;
                 unsigned ph = 0;
-                unsigned aH[3] = {0u, 0u, 0u};
+                unsigned aH[3];
+#pragma unroll
+                for (int b = 0; b < 3; ++b) aH[b] = ring + (unsigned)b * band_l;
                 bool fresh = true;                        // the current stage has not been waited for yet
 #pragma unroll 1
-                for (int qb = 0; qb < nrows; qb += UQ) {
+                for (int qb = 0; qb < nrows_u; qb += UQ) {
 #pragma unroll
                     for (int u = 0; u < UQ; ++u) {
-                        if (qb + u < nrows) {
+                        if (qb + u < nrows_u) {
+                            const bool live = qb + u < nrows;      // this lane's stream still has rows
                             if (fresh) {
-                                if (!(p.dbg & 1)) mbar_wait(bw + 8u * st, ph);
+                                if (live && !(p.dbg & 1)) mbar_wait(bw + 8u * st, ph);
                                 fresh = false;
 #pragma unroll
                                 for (int b = 0; b < 3; ++b)
@@ -418,7 +431,7 @@ __global__ void __launch_bounds__(SfbT<L>::NT, 1) sfb_tma_kernel(const __grid_co
                             a_low += low_pitch_b;
                             aH[0] += w_b; aH[1] += w_b; aH[2] += w_b;
                             if (++jr == SR || qb + u + 1 == nrows) {   // done with this stage
-                                if (!(p.dbg & 8)) mbar_arrive(be + 8u * st);
+                                if (live && !(p.dbg & 8)) mbar_arrive(be + 8u * st);
                                 jr = 0;
                                 r0 += SR;
                                 fresh = true;

@@ -50,7 +50,7 @@ print("  %-14s median %6.2f us  min %6.2f  max %6.2f" % ("total", np.median(tot)
 ref = t[:, 2]
 if which != "dwt":
     sys.exit(0)
-for lbl, base in (("stream 0: stage landed (service warp)", 8), ("stream 0: stage patched + released", 24), ("stream 0: consumers start stage", 16), ("stream 0: prologue issue k done", 48),
+for lbl, base in (("stream 0: patch(0): enter, landed, rows done, released", 8), ("stream 0: stage patched + released", 24), ("stream 0: consumers start stage", 16), ("stream 0: service start, issue(0) done, issue(1) done", 48),
                   ("stream 0: stage k free again (service warp)", 32), ("stream 0: stage k+D issued", 40)):
     vals = []
     for k in range(8):
