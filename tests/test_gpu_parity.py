@@ -424,12 +424,14 @@ def test_host_pipeline_matches_direct_call():
 
 
 @pytest.mark.parametrize("env", ["B200W_FORCE_TILED=1", "B200W_FORCE_DIRECT=1", "B200W_OWNER=2",
-                                 "B200W_OWNER=2 B200W_OWNER_J0=1", "B200W_OWNER=0"])
+                                 "B200W_OWNER=2 B200W_OWNER_J0=1", "B200W_OWNER=0", "B200W_TMA=0", "B200W_TMA=0 B200W_OWNER=2",
+                                 "B200W_TMA_NOBOXES=1 B200W_OWNER=2", "B200W_TMA_G=2 B200W_TMA_D=2 B200W_OWNER=2"])
 def test_alternative_kernel_paths(env):
     """The same golden / oracle cases through the other implementations of the path (the env switches are read
-    once per process, hence a child pytest): shared-memory tile kernels, plane-resident kernels, direct kernels,
-    the owner kernel forced onto every multi-level shape that fits (also starting at level 1 behind a chain
-    launch), and the ticketed chain kernels alone."""
+    once per process, hence a child pytest): shared-memory tile kernels, direct kernels, the owner kernels forced
+    onto every multi-level shape that fits (TMA-staged ones first; B200W_TMA=0: the cp.async ones, also starting at
+    level 1 behind a chain launch), the ticketed chain kernels alone, the TMA kernels with row-by-row staging of the
+    extension rows / with few streams and the shallowest ring."""
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     child_env = dict(os.environ)
