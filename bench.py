@@ -76,6 +76,17 @@ def ncu_traffic(workload, kernel):
     return None
 
 
+def host_copy_bound(n_gpus):
+    """Measured pinned-memory copy bandwidth of the box with `n_gpus` ranks copying at once, both directions busy
+    (profiles/pcie_probe.json, written from tools/pcie_probe.py runs under torchrun): GB/s per rank per direction."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "pcie_probe.json")) as fh:
+            e = json.load(fh).get(str(n_gpus))
+        return (float(e["duplex_gbs_per_rank_per_direction"]), e.get("source")) if e else (None, None)
+    except (OSError, ValueError, KeyError):
+        return None, None
+
+
 def level_sizes(h, w, L, J, mode):
     out = []
     for _ in range(J):
@@ -455,7 +466,7 @@ def ssim_kernels(sets, px, nsets, reps):
         ceil_px_s = fma_per_s / fma_px
         out[key] = {"s": t, "GB/s": nbytes * px / t / 1e9, "bytes": nbytes * px, "Gpx/s": px / t / 1e9,
                     "fp32_ceiling_GB/s": nbytes * ceil_px_s / 1e9,
-                    "fp32_note": "%d FP32 FMA-class instructions per pixel on %d SMs x 128 lanes x %d MHz" % (fma_px, sms, mhz),
+                    "fp32_note": "%d FP32-pipe lane operations per pixel (FFMA2 = 2) on %d SMs x 128 lanes x %d MHz" % (fma_px, sms, mhz),
                     "sass": __import__("b200wave")._cabi.recent_kernels(1)[0]}
     return out
 
@@ -647,6 +658,12 @@ def main():
                           "steps": e2e_steps,
                           "api": "b200wave.HostPipeline(step, chunks=%d): pinned host -> H2D | kernels | D2H overlapped "
                                  "on three streams" % len(pipe.bounds)}
+            gbs, src = host_copy_bound(world)
+            if gbs:   # the step cannot be faster than its own copies at the box's measured duplex copy rate
+                bound_ms = max(h2d, d2h) / (gbs * 1e9) * 1e3
+                res["e2e"]["host_bound"] = {"duplex_gbs_per_rank_per_direction": gbs, "bound_ms_per_step": bound_ms,
+                                            "source": src}
+                res["e2e"]["frac_of_host_bound"] = bound_ms / (e2e_ms / e2e_steps)
             del pipe, host_in
         if rank == 0:
             graphs = None   # free the pools before the kernel timings allocate their own

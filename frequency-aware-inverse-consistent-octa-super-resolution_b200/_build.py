@@ -58,6 +58,36 @@ def is_fresh():
         return fh.read().strip() == _source_hash()
 
 
+BOUNDS_LIB_PATH = os.path.join(LIB_DIR, "libb200wave_bounds.so")
+# the sources compiled with -DB200W_BOUNDS: the kernels that run by default (stream, owner and TMA kernels)
+BOUNDS_SOURCES = ["dwt_stream_afb.cu", "dwt_stream_sfb.cu", "dwt_tma_afb.cu", "dwt_tma_sfb.cu"]
+
+
+def build_bounds(verbose=False):
+    """The B200W_BOUNDS debug build (device-side bounds checks on every shared / global access of the DWT kernels, see
+    csrc/common.cuh) as a second library, ``_lib/libb200wave_bounds.so``; used by tests through B200W_LIBRARY."""
+    nvcc = find_nvcc()
+    if nvcc is None:
+        raise RuntimeError("nvcc not found")
+    os.makedirs(LIB_DIR, exist_ok=True)
+    stamp = os.path.join(LIB_DIR, "libb200wave_bounds.stamp")
+    want = _source_hash() + "+bounds"
+    if os.path.exists(BOUNDS_LIB_PATH) and os.path.exists(stamp) and open(stamp).read().strip() == want:
+        return BOUNDS_LIB_PATH
+    build()   # the sources without checks (api, tile / direct kernels, SSIM, ...) come from the regular build
+    import fcntl
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            path = _build_locked(nvcc, verbose, extra=["-DB200W_BOUNDS"], out_path=BOUNDS_LIB_PATH, suffix=".bounds.o",
+                                 only=BOUNDS_SOURCES)
+            with open(stamp, "w") as fh:
+                fh.write(want)
+            return path
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
 def build(force=False, verbose=False):
     """Compile every ``csrc/*.cu`` into ``_lib/libb200wave.so``; returns its path.  Safe against concurrent callers
     (one process per GPU under torchrun): an exclusive file lock serialises them and the library is moved into place
@@ -79,12 +109,15 @@ def build(force=False, verbose=False):
             fcntl.flock(lock, fcntl.LOCK_UN)
 
 
-def _build_locked(nvcc, verbose):
+def _build_locked(nvcc, verbose, extra=(), out_path=None, suffix=".o", only=None):
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
+        if only is not None and src not in only:   # a variant build reuses the regular object of this source
+            objs.append(os.path.join(LIB_DIR, src.replace(".cu", ".o")))
+            continue
+        obj = os.path.join(LIB_DIR, src.replace(".cu", suffix))
+        cmd = [nvcc] + NVCC_FLAGS + list(extra) + ["-I", INCLUDE, "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
         if src == "api.cu":   # the binary carries the hash of the tree it was built from (b200w_build_hash)
             cmd.insert(1, '-DB200W_BUILD_HASH="%s"' % _source_hash())
         if verbose:
@@ -98,6 +131,15 @@ def _build_locked(nvcc, verbose):
             print(out, file=sys.stderr)
         if pr.returncode != 0:
             raise RuntimeError("nvcc failed on %s:\n%s" % (src, out))
+    if out_path is not None:
+        tmp = out_path + ".tmp.%d" % os.getpid()
+        link = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
+                "-Xcompiler", "-fPIC", "-o", tmp] + objs
+        res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("link failed:\n%s" % res.stdout)
+        os.replace(tmp, out_path)
+        return out_path
     tmp = LIB_PATH + ".tmp.%d" % os.getpid()
     link = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
             "-Xcompiler", "-fPIC", "-o", tmp] + objs
@@ -111,4 +153,7 @@ def _build_locked(nvcc, verbose):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--bounds" in sys.argv:
+        print(build_bounds(verbose="-v" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

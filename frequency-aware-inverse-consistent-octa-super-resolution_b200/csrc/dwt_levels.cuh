@@ -160,6 +160,35 @@ int launch_sfb_owner(const SfbOwnerParams& op, int L, cudaStream_t st);
 // CUDA graph a kernel -> memset -> kernel sequence costs several microseconds of engine switching)
 int zero_sync_words(unsigned* words, size_t n, cudaStream_t st);
 
+// B200W_BOUNDS build: the global buffers a chain launch may touch (see common.cuh); no-ops otherwise
+#ifdef B200W_BOUNDS
+static inline void afb_register_bounds(const AfbParams& p, cudaStream_t st) {
+    BoundsList b;
+    for (int j = 0; j < p.J; ++j) {
+        const AfbLevel& lv = p.lv[j];
+        b.add(lv.x, sizeof(float) * (size_t)((long long)(p.planes - 1) * lv.x_ps + (long long)(lv.Hreal - 1) * lv.x_rs + lv.Wreal));
+        if (lv.low) b.add(lv.low, sizeof(float) * (size_t)((long long)(p.planes - 1) * lv.low_ps + (long long)(lv.Ho - 1) * lv.low_rs + lv.Wo));
+        if (lv.highs) b.add(lv.highs, sizeof(float) * (size_t)p.planes * 3 * lv.Ho * lv.Wo);
+    }
+    if (p.ticket) b.add(p.ticket, sizeof(unsigned) * ((size_t)p.J * p.planes + 1));
+    bounds_set(b, st);
+}
+static inline void sfb_register_bounds(const SfbParams& p, cudaStream_t st) {
+    BoundsList b;
+    for (int c = 0; c < p.J; ++c) {
+        const SfbLevel& lv = p.lv[c];
+        b.add(lv.low, sizeof(float) * (size_t)((long long)(p.planes - 1) * lv.low_ps + (long long)(lv.h - 1) * lv.low_rs + lv.w));
+        if (lv.highs) b.add(lv.highs, sizeof(float) * (size_t)p.planes * 3 * lv.h * lv.w);
+        b.add(lv.y, sizeof(float) * (size_t)((long long)(p.planes - 1) * lv.y_ps + (long long)(lv.out_h - 1) * lv.y_rs + lv.out_w));
+    }
+    if (p.ticket) b.add(p.ticket, sizeof(unsigned) * ((size_t)p.J * p.planes + 1));
+    bounds_set(b, st);
+}
+#else
+static inline void afb_register_bounds(const AfbParams&, cudaStream_t) {}
+static inline void sfb_register_bounds(const SfbParams&, cudaStream_t) {}
+#endif
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 

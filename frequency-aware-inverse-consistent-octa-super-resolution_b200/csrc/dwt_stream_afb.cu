@@ -148,6 +148,7 @@ struct OwnRows {
 };
 
 __device__ __forceinline__ float4 lds128(unsigned addr) {
+    B200W_CHK_S(addr, 16);
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
@@ -219,6 +220,7 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
                     }
                 } else {
                     float4* d = ring + (st * 2 + e) * RP + slot;
+                    B200W_CHK(d, 16 * (ncopy + nextra));
                     d[0] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (Q == 2 && ncopy == 2) d[1] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (run_last) {
@@ -302,7 +304,7 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
 #pragma unroll
                             for (int k = 0; k < NVQ; ++k) {
                                 float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (Q == 1 || k < nv) t = src[e * RP + k];
+                                if (Q == 1 || k < nv) { B200W_CHK(src + e * RP + k, 16); t = src[e * RP + k]; }
                                 v[e][4 * k] = t.x; v[e][4 * k + 1] = t.y; v[e][4 * k + 2] = t.z; v[e][4 * k + 3] = t.w;
                             }
                     }
@@ -325,6 +327,7 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
                                 float* d0 = q0 + 2 * u;
                                 float* d1 = q1 + 2 * u;
                                 if (st_low) {
+                                    B200W_CHK_A(d0, 8, v2lo ? 8 : 4);
                                     if (v2lo) {
                                         *reinterpret_cast<float2*>(d0) = s[0];
                                     } else {
@@ -332,6 +335,7 @@ __device__ __forceinline__ void afb_ring_cta(const AfbParams& p, const AfbLevel&
                                     }
                                 }
                                 if (hi_row) {
+                                    B200W_CHK(d1, 8); B200W_CHK(d1 + band, 8); B200W_CHK(d1 + 2 * band, 8);
                                     const float2 lh = ffma2(s[1], hsc, hsh), hl = ffma2(s[2], hsc, hsh), hh = ffma2(s[3], hsc, hsh);
                                     if (v2hi) {
                                         *reinterpret_cast<float2*>(d1) = lh;
@@ -416,7 +420,7 @@ __device__ __forceinline__ void afb_border_item(const AfbParams& p, const AfbLev
             // would lie before the buffer
             const float* rowp = xp + (long long)max(sr, OWNER ? own.src_row0 : 0) * lv.x_rs;
 #pragma unroll
-            for (int j = 0; j < L; ++j) v[jj][j] = rowp[max(cidx[j], 0)];
+            for (int j = 0; j < L; ++j) { B200W_CHK(rowp + max(cidx[j], 0), 4); v[jj][j] = rowp[max(cidx[j], 0)]; }
         }
 #pragma unroll
         for (int jj = 0; jj < CH; ++jj) {
@@ -438,9 +442,13 @@ __device__ __forceinline__ void afb_border_item(const AfbParams& p, const AfbLev
     }
     const size_t band = (size_t)lv.Ho * lv.Wo;
     const size_t o = (size_t)i * lv.Wo + k;
-    if (lv.st_low) lv.low[(long long)plane * lv.low_ps + (long long)i * lv.low_rs + k] = ll;
+    if (lv.st_low) {
+        B200W_CHK(lv.low + (long long)plane * lv.low_ps + (long long)i * lv.low_rs + k, 4);
+        lv.low[(long long)plane * lv.low_ps + (long long)i * lv.low_rs + k] = ll;
+    }
     if (lv.st_hi && (!OWNER || (i >= own.h0 && i < own.h1))) {
         float* hip = lv.highs + (size_t)plane * 3 * band + o;
+        B200W_CHK(hip, 4); B200W_CHK(hip + band, 4); B200W_CHK(hip + 2 * band, 4);
         hip[0] = fmaf(lh, lv.hi_scale, lv.hi_shift);
         hip[band] = fmaf(hl, lv.hi_scale, lv.hi_shift);
         hip[2 * band] = fmaf(hh, lv.hi_scale, lv.hi_shift);
@@ -692,6 +700,7 @@ static int launch_afb_stream_t(AfbParams& p, int sms, cudaStream_t st) {
         cudaMemcpyToSymbolAsync(g_timeline, &tl, sizeof(tl), 0, cudaMemcpyHostToDevice, st);
     }
 #endif
+    afb_register_bounds(p, st);
     afb_stream_kernel<L, S><<<(unsigned)base, kStreamNT, C::smem, st>>>(p);
     note_launch("afb_stream_kernel");
     const cudaError_t e = cudaGetLastError();
@@ -857,6 +866,7 @@ static int launch_afb_owner_t(const AfbOwnerParams& op, cudaStream_t st) {
         cudaMemcpyToSymbolAsync(g_timeline, &tl, sizeof(tl), 0, cudaMemcpyHostToDevice, st);
     }
 #endif
+    afb_register_bounds(op.p, st);
     const cudaError_t le = launch_pdl(afb_owner_kernel<L, S>, (unsigned)(op.p.planes * op.parts), NT, floats * 4, st, op);
     note_launch("afb_owner_kernel");
     const cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();

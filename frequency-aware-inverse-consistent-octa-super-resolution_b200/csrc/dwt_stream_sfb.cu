@@ -81,11 +81,13 @@ struct SfbOwnRows {
 };
 
 __device__ __forceinline__ float2 lds64(unsigned addr) {
+    B200W_CHK_S(addr, 8);
     float2 v;
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ float lds32(unsigned addr) {
+    B200W_CHK_S(addr, 4);
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
@@ -157,6 +159,8 @@ __device__ __forceinline__ void sfb_ring_cta(const SfbParams& p, const SfbLevel&
                     }
                 } else {
                     float2* d = ring + (st * 4 + b) * C::RPB + slot;
+                    B200W_CHK(d, 8);
+                    if (run_last) B200W_CHK(d + NS - 1, 8);
                     d[0] = make_float2(0.f, 0.f);
                     if (run_last) {
 #pragma unroll
@@ -209,6 +213,7 @@ __device__ __forceinline__ void sfb_ring_cta(const SfbParams& p, const SfbLevel&
                 for (int b = SMEM_LOW ? 1 : 0; b < 4; ++b)
 #pragma unroll
                     for (int k = 0; k < NS; ++k) {
+                        B200W_CHK(src + b * C::RPB + k, 8);
                         const float2 v = src[b * C::RPB + k];
                         c[b][2 * k] = v.x;
                         c[b][2 * k + 1] = v.y;
@@ -277,6 +282,7 @@ __device__ __forceinline__ void sfb_ring_cta(const SfbParams& p, const SfbLevel&
                         const int row = nrow + r;
                         if (row >= row_lo && row < row_hi) {
                             float* d = yq + r * y_rs;
+                            B200W_CHK_A(d, 16, yv == 4 ? 16 : (yv == 2 ? 8 : 4));
                             if (yv == 4) {
                                 *reinterpret_cast<float4*>(d) = make_float4(s[2 * r].x, s[2 * r].y, s[2 * r + 1].x, s[2 * r + 1].y);
                             } else if (yv == 2) {
@@ -351,6 +357,8 @@ __device__ __forceinline__ void sfb_border_item(const SfbParams& p, const SfbLev
 #pragma unroll
             for (int u = 0; u < H2; ++u) {
                 const int col = max(kc[u], 0);
+                B200W_CHK(lp + col, 4);
+                if (has_hi) { B200W_CHK(hp + col, 4); B200W_CHK(hp + band + col, 4); B200W_CHK(hp + 2 * band + col, 4); }
                 v[uu][0][u] = lp[col];
                 v[uu][1][u] = has_hi ? hp[col] : 0.f;
                 v[uu][2][u] = has_hi ? hp[band + col] : 0.f;
@@ -376,6 +384,7 @@ __device__ __forceinline__ void sfb_border_item(const SfbParams& p, const SfbLev
             }
         }
     }
+    B200W_CHK(lv.y + (long long)plane * lv.y_ps + (long long)nH * lv.y_rs + nW, 4);
     lv.y[(long long)plane * lv.y_ps + (long long)nH * lv.y_rs + nW] = y;
 }
 
@@ -677,6 +686,7 @@ static int launch_sfb_owner_t(const SfbOwnerParams& op, cudaStream_t st) {
         cudaMemcpyToSymbolAsync(g_sfb_timeline, &tl, sizeof(tl), 0, cudaMemcpyHostToDevice, st);
     }
 #endif
+    sfb_register_bounds(op.p, st);
     const cudaError_t le = launch_pdl(sfb_owner_kernel<L, S2V>, (unsigned)(op.p.planes * op.parts), NT, smem, st, op);
     note_launch("sfb_owner_kernel");
     const cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();
@@ -757,6 +767,7 @@ static int launch_sfb_stream_t(SfbParams& p, int sms, cudaStream_t st) {
         const int rc = zero_sync_words(p.ticket, (size_t)p.J * p.planes + 1, st);
         if (rc) return rc;
     }
+    sfb_register_bounds(p, st);
     sfb_stream_kernel<L, S2V><<<(unsigned)base, kStreamNT, SfbSmem<L>::value, st>>>(p);
     note_launch("sfb_stream_kernel");
     const cudaError_t e = cudaGetLastError();

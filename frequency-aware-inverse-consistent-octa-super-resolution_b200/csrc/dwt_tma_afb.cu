@@ -72,19 +72,23 @@ struct RegTaps {
 };
 
 __device__ __forceinline__ float4 lds128t(unsigned addr) {
+    B200W_CHK_S(addr, 16);
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ float lds32t(unsigned addr) {
+    B200W_CHK_S(addr, 4);
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ void sts32t(unsigned addr, float v) {
+    B200W_CHK_S(addr, 4);
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 __device__ __forceinline__ void sts64t(unsigned addr, float2 v) {
+    B200W_CHK_S(addr, 8);
     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
 }
 
@@ -205,6 +209,7 @@ __device__ __forceinline__ void afbt_store(const float2* s, AfbtOut& o) {
         if (!LAST) {
             if (!(o.dbg & 32)) sts64t(o.ll_s, s[0]);
         } else if (g) {
+            B200W_CHK(o.low, o.c1ok ? 8 : 4);
             if (o.low_vec2) {
                 *reinterpret_cast<float2*>(o.low) = s[0];
             } else {
@@ -213,6 +218,7 @@ __device__ __forceinline__ void afbt_store(const float2* s, AfbtOut& o) {
             }
         }
         if (g && !(o.dbg & 16)) {
+            B200W_CHK(o.hi, o.c1ok ? 8 : 4); B200W_CHK(o.hi + o.band, o.c1ok ? 8 : 4); B200W_CHK(o.hi + 2 * o.band, o.c1ok ? 8 : 4);
             if (o.vec2) {
                 *reinterpret_cast<float2*>(o.hi) = s[1];
                 *reinterpret_cast<float2*>(o.hi + o.band) = s[2];
@@ -334,6 +340,8 @@ __global__ void __launch_bounds__(AfbT<L, OFF>::NT, 1) afb_tma_kernel(const __gr
                 const unsigned dst = ring + (unsigned)st * stage_b;
                 if (boxes) {   // rows outside the tensor are zero-filled by the copy engine
                     mbar_expect_tx(full, stage_b);
+                    B200W_CHK_S(dst, 16);
+                    B200W_CHK_S(dst + stage_b - 16, 16);
                     for (int t = 0; t < nstrips; ++t)
                         tma_load_3d(dst + (unsigned)t * srbw4, &p.map_full, full, 4 * t * cps - hl, r_start + k * SR, plane);
                     return;
@@ -367,6 +375,7 @@ __global__ void __launch_bounds__(AfbT<L, OFF>::NT, 1) afb_tma_kernel(const __gr
                 if (k == 0) SVC_MARK(8, 2);
 #pragma unroll 2
                 for (int it = lane; it < npatch; it += 32) {
+                    B200W_CHK(cf + 2 * it, 8);
                     const int2 ds = *reinterpret_cast<const int2*>(cf + 2 * it);
                     if (ds.y >= 0) sts32t(base + (unsigned)ds.x, lds32t(base + (unsigned)ds.y));
                 }
@@ -437,6 +446,7 @@ __global__ void __launch_bounds__(AfbT<L, OFF>::NT, 1) afb_tma_kernel(const __gr
                 if (!(p.dbg & 2))
 #pragma unroll
                 for (int u = 0; u < PS; ++u) {
+                    B200W_CHK(rp + k * PS + u, 8);
                     const int2 ro = rp[k * PS + u];
                     float v[2][NE];
                     afbt_load<L, OFF>(v, lane_ring + (unsigned)ro.x, lane_ring + (unsigned)ro.y);
@@ -509,6 +519,7 @@ __global__ void __launch_bounds__(AfbT<L, OFF>::NT, 1) afb_tma_kernel(const __gr
 #pragma unroll
             for (int u = 0; u < UQ; ++u) {
                 if (qb + u < npairs) {
+                    B200W_CHK(rt + 2 * (qb + u), 8);
                     const int2 ro = *reinterpret_cast<const int2*>(rt + 2 * (qb + u));
                     float v[2][NE];
                     afbt_load<L, OFF>(v, lane_b + (unsigned)ro.x, lane_b + (unsigned)ro.y);
@@ -851,6 +862,17 @@ static int launch_afb_tma_t(const AfbTmaParams& tp, cudaStream_t st) {
         cudaMemsetAsync(tl, 0, sizeof(unsigned long long) * 64 * ncta, st);
         tpl.timeline = tl;
     }
+#ifdef B200W_BOUNDS
+    {
+        BoundsList b;
+        for (int j = 0; j < tp.J; ++j) {
+            const AfbTmaLevel& lv = tp.lv[j];
+            b.add(lv.highs, sizeof(float) * (size_t)tp.planes * 3 * lv.Ho * lv.Wo);
+            if (lv.low) b.add(lv.low, sizeof(float) * (size_t)tp.planes * lv.Ho * lv.Wo);
+        }
+        bounds_set(b, st);
+    }
+#endif
     const cudaError_t le = launch_pdl(afb_tma_kernel<L, OFF>, (unsigned)ncta, C::NT, (size_t)tp.smem_bytes, st, tpl);
     note_launch("afb_tma_kernel");
     const cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();

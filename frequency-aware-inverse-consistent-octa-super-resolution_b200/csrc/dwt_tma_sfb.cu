@@ -44,16 +44,19 @@ struct SfbT {
 };
 
 __device__ __forceinline__ float2 lds64s(unsigned addr) {
+    B200W_CHK_S(addr, 8);
     float2 v;
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ float lds32s(unsigned addr) {
+    B200W_CHK_S(addr, 4);
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ void sts128s(unsigned addr, float4 v) {
+    B200W_CHK_S(addr, 16);
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
@@ -177,6 +180,7 @@ __device__ __forceinline__ void sfbt_store(const float2* s, SfbtOut& o) {
                 sts128s(o.y_s + (unsigned)r * o.y_pitch_b, v);
             } else {
                 float* d = o.y + (long long)r * o.y_rs;
+                B200W_CHK(d, 4 * (o.ncol > 0 ? o.ncol : 1));
                 if (o.vec4) {
                     *reinterpret_cast<float4*>(d) = v;
                 } else {
@@ -625,6 +629,18 @@ static int launch_sfb_tma_t(const SfbTmaParams& tp, cudaStream_t st) {
         cudaMemsetAsync(tl, 0, sizeof(unsigned long long) * 64 * ncta, st);
         tpl.timeline = tl;
     }
+#ifdef B200W_BOUNDS
+    {
+        BoundsList b;
+        for (int c = 0; c < tp.J; ++c) {
+            const SfbTmaPos& ps = tp.pos[c];
+            b.add(ps.highs, sizeof(float) * (size_t)tp.planes * 3 * ps.h * ps.w);
+            if (ps.y) b.add(ps.y, sizeof(float) * (size_t)tp.planes * ps.out_h * ps.out_w);
+        }
+        b.add(tp.yl, sizeof(float) * (size_t)tp.planes * tp.pos[0].h * tp.pos[0].w);
+        bounds_set(b, st);
+    }
+#endif
     const cudaError_t le = launch_pdl(sfb_tma_kernel<L>, (unsigned)ncta, C::NT, (size_t)tp.smem_bytes, st, tpl);
     note_launch("sfb_tma_kernel");
     const cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();

@@ -8,6 +8,9 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#ifdef __CUDACC__
+#include "common.cuh"   // B200W_CHK / B200W_CHK_S (no-ops unless -DB200W_BOUNDS)
+#endif
 
 namespace b200w {
 
@@ -89,6 +92,10 @@ __device__ __forceinline__ void tma_load_1d(unsigned dst, const CUtensorMap* map
 }
 // plain bulk copy (no tensor map): `bytes` contiguous bytes, source / destination / size multiples of 16 (UBLKCP)
 __device__ __forceinline__ void bulk_load(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    B200W_CHK_S(dst, 16);
+    B200W_CHK_S(dst + bytes - 16, 16);
+    B200W_CHK(src, 16);
+    B200W_CHK(reinterpret_cast<const char*>(src) + bytes - 16, 16);
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(src)), "r"(bytes), "r"(bar) : "memory");
 }

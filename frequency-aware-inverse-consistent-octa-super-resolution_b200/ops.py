@@ -613,12 +613,15 @@ ssim_bwd = torch.ops.b200wave.ssim_bwd
 
 def ssim_bench_kernels(sets, win):
     """The kernels one SSIM forward + backward step launches, for bench.py's per-kernel timing: yields
-    (name, fn(i), algorithmic bytes per pixel, FP32 FMA-class instructions per pixel).  ``sets`` = [(img1, img2), ...]."""
+    (name, fn(i), algorithmic bytes per pixel, FP32-pipe lane operations per pixel).  ``sets`` = [(img1, img2), ...].
+    Lane operations: a packed FFMA2 occupies the FP32 pipe for two lanes' worth (tools/micro/ffma2.cu), so it counts 2.
+    Forward (4 moments): horizontal 4 x 12 (11 taps in 6 pairs) + 3 products + 4 pair sums, vertical 4 x 11, SSIM map +
+    3 derivative maps 33 = 132.  Backward (3 maps): horizontal 3 x 12 + 3, vertical 4 x 11 (the 4th lane idles), 6 = 89."""
     n = len(sets)
     saved = [ssim_fwd(s[0].detach(), s[1], win, True, 3)[1] for s in sets]
     gout = torch.ones((), device=sets[0][0].device)
     return [
-        ("ssim_fwd", lambda i: ssim_fwd(sets[i % n][0].detach(), sets[i % n][1], win, True, 3), 4 * (2 + 3), 120),
+        ("ssim_fwd", lambda i: ssim_fwd(sets[i % n][0].detach(), sets[i % n][1], win, True, 3), 4 * (2 + 3), 132),
         ("ssim_bwd", lambda i: ssim_bwd(sets[i % n][0].detach(), sets[i % n][1], saved[i % n], gout, win, True, False),
-         4 * (5 + 1), 66),
+         4 * (5 + 1), 89),
     ]

@@ -465,6 +465,41 @@ def test_large_planes_other_policies(env):
     assert res.returncode == 0, res.stdout[-3000:]
 
 
+@pytest.mark.parametrize("env", ["", "B200W_TMA=0", "B200W_OWNER=0"])
+def test_bounds_build(env):
+    """The B200W_BOUNDS debug build of the library (device-side checks of every shared-memory access, staged copy and
+    global store of the stream / owner / TMA kernels against the CTA's shared-memory size and the buffers the launch
+    was given; a violation traps) through the golden, owner-shape and one large-plane case: the in-tree substitute for
+    compute-sanitizer, which is closed on this pool.  The library is built by `python -m b200wave._build --bounds`
+    (minutes of nvcc time, so it is not part of the default build; it travels with the snapshot)."""
+    import subprocess
+    from b200wave import _build
+    stamp = os.path.join(_build.LIB_DIR, "libb200wave_bounds.stamp")
+    fresh = os.path.exists(_build.BOUNDS_LIB_PATH) and os.path.exists(stamp) and \
+        open(stamp).read().strip() == _build._source_hash() + "+bounds"
+    if not fresh:
+        if os.environ.get("B200W_BUILD_BOUNDS") == "1" and _build.find_nvcc():
+            _build.build_bounds()
+        else:
+            pytest.skip("libb200wave_bounds.so is missing or stale: python -m b200wave._build --bounds")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    child_env = dict(os.environ)
+    child_env["B200W_LIBRARY"] = _build.BOUNDS_LIB_PATH
+    for kv in env.split():
+        k, v = kv.split("=")
+        child_env[k] = v
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-x",
+                          "-m", "gpu", "-k", "golden_dwt or golden_idwt or owner_kernel or 1024-db4-symmetric-J5 or "
+                          "1024-db1-zero-J5 or sweep_batch", "-p", "no:cacheprovider"],
+                         cwd=root, env=child_env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                         timeout=2400)
+    if res.returncode != 0:   # the device printf repeats per thread: show the first few violations and pytest's summary
+        lines = res.stdout.splitlines()
+        hits = [ln.strip() for ln in lines if "B200W_BOUNDS" in ln][:6]
+        tail = [ln for ln in lines if ln.startswith(("FAILED", "ERROR")) or " passed" in ln or " failed" in ln][-4:]
+        pytest.fail("\n".join(hits + tail) or res.stdout[-3000:])
+
+
 FREQ_CASES = load_freq_cases()
 
 
