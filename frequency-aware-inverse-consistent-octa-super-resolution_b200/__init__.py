@@ -22,7 +22,7 @@ from .hostpipe import HostPipeline
 from . import freq  # noqa: F401  (utils.high_pass / low_pass)
 from . import fsd  # noqa: F401  (FS_Discriminator*.filter_wavelet)
 from . import losses  # noqa: F401  (TVLoss)
-from .losses import TVLoss
+from .losses import TVLoss, phase_consistency_loss
 
 __version__ = "0.1.0"
 
@@ -32,4 +32,4 @@ DWT2D = DWT
 IDWT2D = IDWT
 
 __all__ = ["DWTForward", "DWTInverse", "DWT", "IDWT", "DWT2D", "IDWT2D", "SSIM", "ssim", "lowlevel",
-           "Wavelet", "wavelist", "HostPipeline", "TVLoss", "__version__"]
+           "Wavelet", "wavelist", "HostPipeline", "TVLoss", "phase_consistency_loss", "__version__"]

@@ -50,6 +50,9 @@ SYMBOLS = {
     "b200w_tv_workspace_bytes": (_sz, [_i, _i]),
     "b200w_tv_fwd_f32": (_i, [_vp, _i, _i, _i, _vp, _sz, _vp, _vp]),
     "b200w_tv_bwd_f32": (_i, [_vp, _vp, ctypes.c_float, ctypes.c_float, _i, _i, _i, _vp, _vp]),
+    "b200w_phase_workspace_bytes": (_sz, [_i, _i, _i]),
+    "b200w_phase_sums_c64": (_i, [_vp, _vp, _i, _i, _i, ctypes.c_float, _vp, _sz, _vp, _vp]),
+    "b200w_phase_grad_c64": (_i, [_vp, _vp, _i, _i, _i, ctypes.c_float, _vp, _vp, ctypes.c_float, _vp, _vp, _vp]),
     "b200w_kernel_launches": (ctypes.c_ulonglong, []),
     "b200w_kernel_log": (ctypes.c_char_p, [_i]),
     "b200w_build_hash": (ctypes.c_char_p, []),

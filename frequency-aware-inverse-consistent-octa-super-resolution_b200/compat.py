@@ -62,7 +62,8 @@ def patch_model(model_module):
     """Swap ``FS_DiscriminatorA.filter_wavelet`` / ``FS_DiscriminatorB.filter_wavelet`` of an already imported
     reference ``model`` module (``model.py:166-179, 222-235``) for the fused analysis-kernel epilogue in
     ``b200wave.fsd``.  The methods keep reading ``self.DWT2`` (its tap buffers and mode) and ``self.cs``, so the
-    discriminators' constructors, state dicts and ``forward`` are untouched."""
+    discriminators' constructors, state dicts and ``forward`` are untouched.  ``model.TVLoss`` and
+    ``model.phase_consistency_loss`` (``model.py:17-58``) are replaced by the fused versions in ``b200wave.losses``."""
     from b200wave import fsd
     from b200wave.dwt import lowlevel
 
@@ -75,4 +76,8 @@ def patch_model(model_module):
 
     model_module.FS_DiscriminatorA.filter_wavelet = make("A")
     model_module.FS_DiscriminatorB.filter_wavelet = make("B")
+    # the reduction-style losses beside the path (model.py:17-58, constructed at train.py:94,98)
+    from b200wave import losses
+    model_module.TVLoss = losses.TVLoss
+    model_module.phase_consistency_loss = losses.phase_consistency_loss
     return model_module

@@ -55,6 +55,84 @@ __global__ void __launch_bounds__(256) sign_mul_kernel(const float* __restrict__
     }
 }
 
+// ---- phase_consistency_loss (model.py:36-58): -cos(a_x, a_y), a = m * log|fft2(.)| over one (C, rows, cols) image,
+// m the radius-5 Gaussian high-pass mask.  The reference shifts both spectra the same way before flattening, which
+// the cosine does not see; the inputs are real, so |F| is even and the half spectrum of rfft2 carries every term:
+// a bin of column v stands for itself and its mirror (weight 2) unless it is its own mirror (v = 0, or v = cols/2
+// with cols even: weight 1).  Kernel 1: the three sums <a_x,a_y>, <a_x,a_x>, <a_y,a_y> (per-CTA partials in double,
+// fixed-order final reduction: bit-reproducible).  Kernel 2: the gradient w.r.t. both half spectra.
+__device__ __forceinline__ float phase_mask(unsigned rem, int rows, int cols, int wh, float inv2r2, float* weight) {
+    const int u = (int)(rem / (unsigned)wh), v = (int)(rem - (unsigned)u * (unsigned)wh);
+    const int du = u < rows - rows / 2 ? u : u - rows;
+    *weight = (v == 0 || 2 * v == cols) ? 1.f : 2.f;
+    return 1.f - expf(-(float)(du * du + v * v) * inv2r2);
+}
+
+__global__ void __launch_bounds__(256) phase_sums_kernel(const float2* __restrict__ fx, const float2* __restrict__ fy,
+                                                         int planes, int rows, int cols, int wh, float inv2r2,
+                                                         double* __restrict__ partials) {
+    const unsigned per_plane = (unsigned)rows * (unsigned)wh;
+    const size_t total = (size_t)per_plane * planes;
+    double sxy = 0.0, sxx = 0.0, syy = 0.0;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        float w;
+        const float m = phase_mask((unsigned)(idx % per_plane), rows, cols, wh, inv2r2, &w);
+        const float2 zx = fx[idx], zy = fy[idx];
+        const float ax = m * logf(hypotf(zx.x, zx.y)), ay = m * logf(hypotf(zy.x, zy.y));
+        sxy += (double)(w * ax * ay);
+        sxx += (double)(w * ax * ax);
+        syy += (double)(w * ay * ay);
+    }
+    __shared__ double red[3][8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sxy += __shfl_xor_sync(0xffffffffu, sxy, o);
+        sxx += __shfl_xor_sync(0xffffffffu, sxx, o);
+        syy += __shfl_xor_sync(0xffffffffu, syy, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sxy; red[1][threadIdx.x >> 5] = sxx; red[2][threadIdx.x >> 5] = syy; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += red[threadIdx.x][i];
+        partials[3 * blockIdx.x + threadIdx.x] = t;
+    }
+}
+
+__global__ void phase_finalize_kernel(const double* __restrict__ partials, int nblocks, float* __restrict__ out3) {
+    if (threadIdx.x < 3) {
+        double t = 0.0;
+        for (int i = 0; i < nblocks; ++i) t += partials[3 * i + threadIdx.x];
+        out3[threadIdx.x] = (float)t;
+    }
+}
+
+// L = -sxy / (nx ny), nx = max(sqrt(sxx), eps): dL/da_x = -(a_y - (sxy / nx^2) a_x) / (nx ny) (the norm term only while
+// nx > eps); a = m log|F| gives dL/dF = dL/da * m * F / |F|^2 in the (d/dRe + i d/dIm) convention autograd uses.
+__global__ void __launch_bounds__(256) phase_grad_kernel(const float2* __restrict__ fx, const float2* __restrict__ fy,
+                                                         int planes, int rows, int cols, int wh, float inv2r2,
+                                                         const float* __restrict__ sums3, const float* __restrict__ grad_out,
+                                                         float eps, float2* __restrict__ gx, float2* __restrict__ gy) {
+    const unsigned per_plane = (unsigned)rows * (unsigned)wh;
+    const size_t total = (size_t)per_plane * planes;
+    const float sxy = sums3[0];
+    const float rx = sqrtf(sums3[1]), ry = sqrtf(sums3[2]);
+    const float nx = fmaxf(rx, eps), ny = fmaxf(ry, eps);
+    const float c = -grad_out[0] / (nx * ny);
+    const float kx = rx > eps ? sxy / (nx * nx) : 0.f, ky = ry > eps ? sxy / (ny * ny) : 0.f;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        float w;
+        const float m = phase_mask((unsigned)(idx % per_plane), rows, cols, wh, inv2r2, &w);
+        const float2 zx = fx[idx], zy = fy[idx];
+        const float hx = hypotf(zx.x, zx.y), hy = hypotf(zy.x, zy.y);
+        const float ax = m * logf(hx), ay = m * logf(hy);
+        const float tx = c * w * m * (ay - kx * ax) / (hx * hx);
+        const float ty = c * w * m * (ax - ky * ay) / (hy * hy);
+        if (gx) gx[idx] = make_float2(tx * zx.x, tx * zx.y);
+        if (gy) gy[idx] = make_float2(ty * zy.x, ty * zy.y);
+    }
+}
+
 static unsigned pointwise_grid(size_t n) {
     size_t g = (n + 255) / 256;
     const size_t cap = 148 * 8;
@@ -95,6 +173,46 @@ extern "C" int b200w_sign_mul_f32(const float* g, const float* x, float* out, si
     if (n == 0) return B200W_OK;
     sign_mul_kernel<<<pointwise_grid(n), 256, 0, (cudaStream_t)stream>>>(g, x, out, n, sign);
     b200w::note_launch("sign_mul_kernel");
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? B200W_OK : set_last_cuda_error(e);
+}
+
+extern "C" size_t b200w_phase_workspace_bytes(int planes, int rows, int cols) {
+    if (planes < 1 || rows < 1 || cols < 1) return 0;
+    return sizeof(double) * 3 * pointwise_grid((size_t)planes * rows * (cols / 2 + 1));
+}
+
+extern "C" int b200w_phase_sums_c64(const void* fx, const void* fy, int planes, int rows, int cols, float radius,
+                                    void* workspace, size_t workspace_bytes, float* out3, void* stream) {
+    if (!fx || !fy || !out3) return B200W_ERR_NULL_POINTER;
+    if (planes < 1 || rows < 1 || cols < 1 || !(radius > 0.f)) return B200W_ERR_BAD_SHAPE;
+    const int wh = cols / 2 + 1;
+    if ((long long)rows * wh > 0x7fffffffLL) return B200W_ERR_BAD_SHAPE;
+    const size_t total = (size_t)planes * rows * wh;
+    const unsigned grid = pointwise_grid(total);
+    if (!workspace || workspace_bytes < sizeof(double) * 3 * grid) return B200W_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    phase_sums_kernel<<<grid, 256, 0, st>>>((const float2*)fx, (const float2*)fy, planes, rows, cols, wh,
+                                            0.5f / (radius * radius), (double*)workspace);
+    b200w::note_launch("phase_sums_kernel");
+    phase_finalize_kernel<<<1, 32, 0, st>>>((const double*)workspace, (int)grid, out3);
+    b200w::note_launch("phase_finalize_kernel");
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? B200W_OK : set_last_cuda_error(e);
+}
+
+extern "C" int b200w_phase_grad_c64(const void* fx, const void* fy, int planes, int rows, int cols, float radius,
+                                    const float* sums3, const float* grad_out, float eps, void* gx, void* gy,
+                                    void* stream) {
+    if (!fx || !fy || !sums3 || !grad_out || (!gx && !gy)) return B200W_ERR_NULL_POINTER;
+    if (planes < 1 || rows < 1 || cols < 1 || !(radius > 0.f)) return B200W_ERR_BAD_SHAPE;
+    const int wh = cols / 2 + 1;
+    if ((long long)rows * wh > 0x7fffffffLL) return B200W_ERR_BAD_SHAPE;
+    const size_t total = (size_t)planes * rows * wh;
+    phase_grad_kernel<<<pointwise_grid(total), 256, 0, (cudaStream_t)stream>>>(
+        (const float2*)fx, (const float2*)fy, planes, rows, cols, wh, 0.5f / (radius * radius), sums3, grad_out, eps,
+        (float2*)gx, (float2*)gy);
+    b200w::note_launch("phase_grad_kernel");
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? B200W_OK : set_last_cuda_error(e);
 }

@@ -22,6 +22,8 @@
  *   b200w_dwt_coeff_len pywt.dwt_coeff_len as called at pw/dwt/lowlevel.py:153
  *   b200w_freq_mask_c64 / b200w_abs_sign_f32 / b200w_sign_mul_f32
  *                       utils.py:71-117  Gaussian low / high pass in the Fourier domain
+ *   b200w_tv_fwd_f32 / b200w_tv_bwd_f32           model.py:17-33  TVLoss
+ *   b200w_phase_sums_c64 / b200w_phase_grad_c64   model.py:36-58  phase_consistency_loss
  *
  * Conventions
  *   - every image pointer is DEVICE memory owned by the caller (torch); the library never
@@ -215,6 +217,23 @@ int b200w_tv_fwd_f32(const float* x, int planes, int H, int W, void* workspace, 
                      float* out2, void* stream);
 int b200w_tv_bwd_f32(const float* x, const float* grad_out, float ch, float cw, int planes, int H, int W,
                      float* dx, void* stream);
+
+/*
+ * phase_consistency_loss, model.py:36-58 (constructed at train.py:94), SURVEY.md 8f row 4: minus the cosine
+ * similarity of a_x = m * log|fft2(x[0])| and a_y = m * log|fft2(y[0])|, m = 1 - exp(-0.5 d^2 / radius^2) the Gaussian
+ * high-pass mask around the spectrum centre (radius 5 in the reference).  `fx`, `fy`: HALF spectra of the real images
+ * (rfft2 layout, (planes, rows, cols/2+1) interleaved complex64); mirrored bins are counted with weight 2.
+ * b200w_phase_sums_c64: out3 = { <a_x,a_y>, <a_x,a_x>, <a_y,a_y> } (device floats; per-CTA partials in double in
+ *   `workspace` = b200w_phase_workspace_bytes(...) bytes, reduced in fixed order).  The loss is
+ *   -out3[0] / (max(sqrt(out3[1]), eps) * max(sqrt(out3[2]), eps))  (torch.cosine_similarity, eps = 1e-8).
+ * b200w_phase_grad_c64: gx, gy (either may be NULL) = grad_out[0] * dLoss/d(fx), d(fy) in the d/dRe + i d/dIm convention
+ *   of torch autograd, same layout as the spectra; `sums3` = out3 of the forward call.
+ */
+size_t b200w_phase_workspace_bytes(int planes, int rows, int cols);
+int b200w_phase_sums_c64(const void* fx, const void* fy, int planes, int rows, int cols, float radius,
+                         void* workspace, size_t workspace_bytes, float* out3, void* stream);
+int b200w_phase_grad_c64(const void* fx, const void* fy, int planes, int rows, int cols, float radius,
+                         const float* sums3, const float* grad_out, float eps, void* gx, void* gy, void* stream);
 
 #ifdef __cplusplus
 }

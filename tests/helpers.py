@@ -98,3 +98,15 @@ def load_tv_cases():
         case["id"] = "%02d-%s-w%g" % (i, "x".join(str(d) for d in case["x"].shape), case["weight"])
         cases.append(case)
     return cases
+
+
+def load_phase_cases():
+    z = np.load(os.path.join(GOLDEN, "phase_cases.npz"))
+    cases = []
+    for i in range(int(z["ncases"])):
+        pre = "p%02d/" % i
+        case = {k[len(pre):]: z[k] for k in z.files if k.startswith(pre)}
+        case["loss"] = float(case["loss"])
+        case["id"] = "%02d-%s" % (i, "x".join(str(d) for d in case["x"].shape))
+        cases.append(case)
+    return cases

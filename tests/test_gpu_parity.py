@@ -15,7 +15,7 @@ import b200wave
 from b200wave import lowlevel
 from oracle import dwt_oracle, freq_oracle, fsd_oracle, ssim_oracle, tv_oracle
 from helpers import (RTOL_F32, case_filters, load_dwt_cases, load_freq_cases, load_fsd_cases, load_ssim_cases,
-                     load_tv_cases, rel_err)
+                     load_phase_cases, load_tv_cases, rel_err)
 
 pytestmark = pytest.mark.gpu
 
@@ -658,6 +658,7 @@ def test_patch_model_swaps_the_discriminator_methods():
     case = [c for c in FSD_CASES if c["variant"] == "A" and c["cs"] == "sum"][0]
     got, x = mod.FS_DiscriminatorA("sum").to(DEV).filter_wavelet(cu(case["x"]), case["norm"])
     assert rel_err(got.cpu(), case["y"][0]) < RTOL_F32
+    assert mod.TVLoss is b200wave.TVLoss and mod.phase_consistency_loss is b200wave.phase_consistency_loss
 
 
 _OWNER_GRID = [((12, 1, 128, 160), w, m, 3) for w in ("haar", "db2", "db3", "db4", "db5", "db8")
@@ -720,6 +721,42 @@ def test_golden_tv_loss(case):
     assert abs(loss.item() - case["loss"]) <= RTOL_F32 * abs(case["loss"])
     loss.backward()
     assert rel_err(x.grad.cpu(), case["dx"]) < RTOL_F32
+
+
+PHASE_CASES = load_phase_cases()
+# fp32 FFT: the log-amplitude of weak bins carries the transform's absolute error (~1e-7 * sqrt(H W) * max|F|), and the
+# gradient divides by |F|^2 once more -- so the input gradients are compared at 2e-4 of their maximum, the value at 1e-5
+PHASE_GRAD_RTOL = 2e-4
+
+
+@pytest.mark.parametrize("case", PHASE_CASES, ids=[c["id"] for c in PHASE_CASES])
+def test_golden_phase_consistency_loss(case):
+    """b200wave.phase_consistency_loss vs the reference module's own value and input gradients (model.py:36-58)."""
+    x, y = cu(case["x"], grad=True), cu(case["y"], grad=True)
+    loss = b200wave.phase_consistency_loss()(x, y)
+    assert loss.dim() == 0
+    assert abs(loss.item() - case["loss"]) <= RTOL_F32
+    loss.backward()
+    assert rel_err(x.grad.cpu(), case["dx"]) < PHASE_GRAD_RTOL
+    assert rel_err(y.grad.cpu(), case["dy"]) < PHASE_GRAD_RTOL
+    if x.shape[0] > 1:      # only the first batch element enters (model.py:52,55)
+        assert float(x.grad[1:].abs().max()) == 0.0
+
+
+def test_phase_consistency_loss_train_size():
+    """The crop size of the training step (train.py: 256 x 256 single-channel) against the oracle; upstream gradient
+    other than 1; identical images give -1."""
+    from oracle import phase_oracle
+    rng = np.random.default_rng(9)
+    xn = rng.random((4, 1, 256, 256)).astype(np.float32)
+    yn = np.clip(xn + 0.1 * rng.standard_normal(xn.shape), 0, 1).astype(np.float32)
+    crit = b200wave.phase_consistency_loss()
+    x, y = cu(xn, grad=True), cu(yn)
+    loss = crit(x, y)
+    assert abs(loss.item() - phase_oracle.phase_consistency_loss(xn, yn)) <= RTOL_F32
+    (loss * 2.5).backward()
+    assert rel_err(x.grad.cpu(), 2.5 * phase_oracle.phase_consistency_grad(xn, yn, 0)) < PHASE_GRAD_RTOL
+    assert abs(crit(cu(xn), cu(xn)).item() + 1.0) < 1e-6
 
 
 def test_tv_loss_full_size_and_scaled_gradient():

@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 
-from oracle import dwt_oracle, freq_oracle, fsd_oracle, ssim_oracle, tv_oracle
+from oracle import dwt_oracle, freq_oracle, fsd_oracle, phase_oracle, ssim_oracle, tv_oracle
 from helpers import (load_dwt_cases, load_freq_cases, load_fsd_cases, load_ssim_cases, load_tv_cases, case_filters,
                      rel_err)
 
@@ -162,3 +162,23 @@ def test_tv_loss_host_logic_without_gpu():
     assert crit.TVLoss_weight == 0.5 and crit._tensor_size(torch.zeros(2, 3, 4, 5)) == 60
     with pytest.raises(RuntimeError, match="CUDA-only"):
         crit(torch.rand(1, 1, 8, 8))
+
+
+PHASE_CASES = __import__("helpers").load_phase_cases()
+
+
+@pytest.mark.parametrize("case", PHASE_CASES, ids=[c["id"] for c in PHASE_CASES])
+def test_phase_oracle_vs_reference(case):
+    """phase_oracle vs the value and both input gradients of the reference's phase_consistency_loss (model.py:36-58)."""
+    assert abs(phase_oracle.phase_consistency_loss(case["x"], case["y"]) - case["loss"]) <= 1e-11
+    assert rel_err(phase_oracle.phase_consistency_grad(case["x"], case["y"], 0), case["dx"]) < 1e-9
+    assert rel_err(phase_oracle.phase_consistency_grad(case["x"], case["y"], 1), case["dy"]) < 1e-9
+
+
+def test_phase_loss_host_logic_without_gpu():
+    """No CPU fallback: CPU tensors are refused loudly, shapes are checked before any device work."""
+    import torch
+    import b200wave
+    crit = b200wave.phase_consistency_loss()
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        crit(torch.rand(1, 1, 8, 8), torch.rand(1, 1, 8, 8))
