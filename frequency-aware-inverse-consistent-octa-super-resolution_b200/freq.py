@@ -14,6 +14,7 @@ Differentiable: the filter is linear and self-adjoint (real, even mask), ``abs``
 import ctypes
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _cabi
 
@@ -101,6 +102,7 @@ class _GaussianSplit(torch.autograd.Function):
         return torch.ops.b200wave_freq.abs_sign(y, float(sign))
 
     @staticmethod
+    @once_differentiable   # the backward kernels have no autograd formula of their own: double backward raises
     def backward(ctx, g):
         (y,) = ctx.saved_tensors
         radius, highpass, sign = ctx.args

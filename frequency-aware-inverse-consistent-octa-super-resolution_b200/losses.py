@@ -16,6 +16,7 @@ CUDA-only, like the rest of the package.
 import ctypes
 
 import torch
+from torch.autograd.function import once_differentiable
 import torch.nn as nn
 
 from . import _cabi
@@ -153,6 +154,7 @@ class _TV(torch.autograd.Function):
         return weight * 2 * (sums[0] / count_h + sums[1] / count_w) / n
 
     @staticmethod
+    @once_differentiable   # the backward kernels have no autograd formula of their own: double backward raises
     def backward(ctx, g):
         (x,) = ctx.saved_tensors
         weight, n, count_h, count_w = ctx.scales
@@ -190,6 +192,7 @@ class _PhaseCos(torch.autograd.Function):
         return -sums[0] / (norms[0] * norms[1])
 
     @staticmethod
+    @once_differentiable   # the backward kernels have no autograd formula of their own: double backward raises
     def backward(ctx, g):
         rx, ry, sums = ctx.saved_tensors
         cols, radius = ctx.geom

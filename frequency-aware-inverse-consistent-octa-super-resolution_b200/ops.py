@@ -18,6 +18,7 @@ mathematical adjoint:
 import ctypes
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _cabi
 
@@ -366,6 +367,7 @@ class DWT2Function(torch.autograd.Function):
         return tuple(outs)
 
     @staticmethod
+    @once_differentiable   # the backward kernels have no autograd formula of their own: double backward raises
     def backward(ctx, gyl, *gyh):
         if not ctx.needs_input_grad[0] or (gyl is None and all(g is None for g in gyh)):
             return (None,) * 7
@@ -417,6 +419,7 @@ class IDWT2Function(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable   # the backward kernels have no autograd formula of their own: double backward raises
     def backward(ctx, dy):
         J = ctx.J
         need_l = ctx.needs_input_grad[5]

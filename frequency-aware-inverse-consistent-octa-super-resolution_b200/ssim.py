@@ -30,7 +30,17 @@ def create_window(window_size, channel):
 _win_cache = {}
 
 
+def _check_window(window_size):
+    """The fused kernel holds an odd window of at most 11 taps (the reference's default and only use, train.py:97).
+    The reference itself accepts any size (an even one yields an (H+1) x (W+1) map); anything else is refused here,
+    loudly and before any device work."""
+    if not isinstance(window_size, int) or window_size < 1 or window_size > 11 or window_size % 2 == 0:
+        raise ValueError("b200wave.SSIM / ssim support odd window sizes 1..11 (got %r): the fused sm_100a kernel is "
+                         "built for the reference's 11-tap Gaussian window and smaller odd ones" % (window_size,))
+
+
 def _win_taps(window_size):
+    _check_window(window_size)
     taps = _win_cache.get(window_size)
     if taps is None:
         taps = tuple(float(v) for v in gaussian(window_size, 1.5).tolist())
@@ -61,6 +71,7 @@ def _ssim(img1, img2, window, window_size, channel, size_average=True):
 class SSIM(torch.nn.Module):
     def __init__(self, window_size=11, size_average=True):
         super(SSIM, self).__init__()
+        _check_window(window_size)
         self.window_size = window_size
         self.size_average = size_average
         self.channel = 1

@@ -148,3 +148,22 @@ def test_compat_aliases_resolve_reference_imports():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_ssim_window_sizes_outside_the_kernel_range_are_refused_at_construction():
+    """the fused kernel holds an odd window <= 11; SSIM(window_size=8) / 15 raise a ValueError naming the
+    supported range instead of failing later inside the C ABI."""
+    import b200wave
+    for w in (8, 15, 0, 12):
+        with pytest.raises(ValueError, match="odd window sizes 1..11"):
+            b200wave.SSIM(window_size=w)
+    assert b200wave.SSIM(window_size=5).window.shape == (1, 1, 5, 5)
+
+
+def test_backwards_are_marked_once_differentiable():
+    """the hand-written backwards call kernels without autograd formulas, so they are declared
+    once-differentiable (a double backward raises instead of silently returning no gradient)."""
+    import inspect
+    from b200wave import ops, losses
+    for fn in (ops.DWT2Function, ops.IDWT2Function, losses._TV, losses._PhaseCos):
+        assert "once_differentiable" in inspect.getsource(fn)
