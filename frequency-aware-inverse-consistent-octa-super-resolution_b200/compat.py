@@ -6,9 +6,9 @@
     import ssim; ssim.SSIM()                                  # -> b200wave.ssim
 
 so that ``model.py`` (``from pytorch_wavelets import DWTForward, DWTInverse``, model.py:4) and ``train.py``
-(``import ssim``-style use at train.py:97) of the reference run unmodified on the CUDA path.  Only the 2-D DWT
-surface is provided (SURVEY.md section 2 marks the 1-D / SWT / DTCWT / scattering parts out of scope); asking
-for anything else raises AttributeError instead of silently falling back.
+(``import ssim``-style use at train.py:97) of the reference run unmodified on the CUDA path.  The 2-D and 1-D DWT
+surfaces are provided (SWT / DTCWT / scattering are out of scope); asking for anything else
+raises AttributeError instead of silently falling back.
 """
 import importlib
 import sys
@@ -17,7 +17,7 @@ import types
 
 def install(force=False):
     import b200wave
-    from b200wave.dwt import lowlevel, transform2d
+    from b200wave.dwt import lowlevel, transform1d, transform2d
     ssim_mod = importlib.import_module("b200wave.ssim")
 
     if not force:
@@ -31,18 +31,21 @@ def install(force=False):
     pw.__b200wave_alias__ = True
     pw.__version__ = "1.3.0+b200wave." + b200wave.__version__
     pw.__path__ = []
-    for name in ("DWTForward", "DWTInverse", "DWT", "IDWT", "DWT2D", "IDWT2D"):
+    for name in ("DWTForward", "DWTInverse", "DWT", "IDWT", "DWT2D", "IDWT2D", "DWT1DForward", "DWT1DInverse", "DWT1D",
+                 "IDWT1D"):
         setattr(pw, name, getattr(b200wave, name))
     dwt = types.ModuleType("pytorch_wavelets.dwt")
     dwt.__b200wave_alias__ = True
     dwt.__path__ = []
     dwt.lowlevel = lowlevel
     dwt.transform2d = transform2d
+    dwt.transform1d = transform1d
     pw.dwt = dwt
     sys.modules["pytorch_wavelets"] = pw
     sys.modules["pytorch_wavelets.dwt"] = dwt
     sys.modules["pytorch_wavelets.dwt.lowlevel"] = lowlevel
     sys.modules["pytorch_wavelets.dwt.transform2d"] = transform2d
+    sys.modules["pytorch_wavelets.dwt.transform1d"] = transform1d
     ssim_mod.__b200wave_alias__ = True
     sys.modules["ssim"] = ssim_mod
     return pw

@@ -97,6 +97,27 @@ class SFB2D(object):
                          _as_taps(g0_col, False), _as_taps(g1_col, False), int(mode), -1, -1)
 
 
+class AFB1D(object):
+    """Single-level 1-D analysis: ``AFB1D.apply(x, h0, h1, mode) -> (x0, x1)`` on (N, C, L) tensors
+    (pw/dwt/lowlevel.py:368-424).  ``h0`` / ``h1`` as stored by ``prep_filt_afb1d`` (time-reversed).  Differentiable
+    w.r.t. ``x`` with the reference's backward (synthesis with the same taps, cropped to the input length)."""
+
+    @staticmethod
+    def apply(x, h0, h1, mode):
+        int_to_mode(mode)
+        return ops.afb1d(x, _as_taps(h0, True), _as_taps(h1, True), int(mode))
+
+
+class SFB1D(object):
+    """Single-level 1-D synthesis: ``SFB1D.apply(low, high, g0, g1, mode) -> y`` (pw/dwt/lowlevel.py:697-743).  As for
+    ``SFB2D``, ``high.grad`` is produced even when ``low`` needs none (the reference returns ``None``, :735)."""
+
+    @staticmethod
+    def apply(low, high, g0, g1, mode):
+        int_to_mode(mode)
+        return ops.sfb1d(low, high, _as_taps(g0, False), _as_taps(g1, False), int(mode), -1)
+
+
 def _four_filters(filts, prep, device=None):
     """Normalise the ``filts`` argument of afb2d / sfb2d to (col_lo, col_hi, row_lo, row_hi) tensors.
     A pair means "same filters on both axes"; raw arrays go through ``prep``; prepared tensors are

@@ -33,6 +33,8 @@ _LIB.define("dwt2(Tensor x, float[] w_lo, float[] w_hi, float[] h_lo, float[] h_
             "-> Tensor[]")
 _LIB.define("idwt2(Tensor yl, Tensor?[] yh, int[] hw, float[] w_lo, float[] w_hi, float[] h_lo, float[] h_hi, int mode, "
             "int[] out_hw) -> Tensor")
+_LIB.define("afb1d(Tensor x, float[] h0, float[] h1, int mode) -> (Tensor, Tensor)")
+_LIB.define("sfb1d(Tensor low, Tensor? high, float[] g0, float[] g1, int mode, int out_len) -> Tensor")
 _LIB.define("ssim_fwd(Tensor img1, Tensor img2, float[] win, bool size_average, int n_maps) -> (Tensor, Tensor)")
 _LIB.define("ssim_bwd(Tensor img1, Tensor img2, Tensor maps, Tensor grad_out, float[] win, bool size_average, "
             "bool need_d2) -> (Tensor, Tensor)")
@@ -489,6 +491,126 @@ def _sfb2d_backward(ctx, dy):
     return dlow, dhighs, None, None, None, None, None, None, None
 
 
+# ------------------------------------------------------------------------------------------- 1-D banks
+def _rows_view(t):
+    """(N, C, L) tensor -> (tensor to keep alive, row stride): rows must be equally spaced with unit sample stride."""
+    n, c, l = t.shape
+    sn, sc, sl = t.stride()
+    ok = (sl == 1 or l == 1) and (n == 1 or c == 1 or sn == c * sc)
+    if not ok:
+        t = t.contiguous()
+        sn, sc, sl = t.stride()
+    return t, (sc if c > 1 else (sn if n > 1 else l))
+
+
+def _afb1d_cuda(x, h0, h1, mode):
+    _check_mode(mode)
+    _require_cuda_f32(x, "afb1d")
+    if x.dim() != 3:
+        raise IndexError("b200wave::afb1d expects a 3-D (N, C, L) tensor, got %d-D" % x.dim())
+    if len(h0) != len(h1):
+        raise RuntimeError("low- and high-pass filters must have the same length")
+    lib = _cabi.load()
+    N, C, n = x.shape
+    m = coeff_len(n, len(h0), mode)
+    lo = torch.empty((N, C, m), device=x.device, dtype=torch.float32)
+    hi = torch.empty((N, C, m), device=x.device, dtype=torch.float32)
+    if lo.numel() == 0:
+        return lo, hi
+    xk, rs = _rows_view(x)
+    a0, _ = _cabi.taps_array(h0)
+    a1, _ = _cabi.taps_array(h1)
+    with torch.cuda.device(x.device):
+        rc = lib.b200w_afb1d_f32(xk.data_ptr(), rs, N * C, n, a0, a1, len(h0), int(mode), lo.data_ptr(), hi.data_ptr(),
+                                 _stream())
+    _cabi.check(rc, _mode_name(mode))
+    return lo, hi
+
+
+def _afb1d_fake(x, h0, h1, mode):
+    N, C, n = x.shape
+    m = coeff_len(n, len(h0), mode)
+    return x.new_empty((N, C, m)), x.new_empty((N, C, m))
+
+
+def _sfb1d_cuda(low, high, g0, g1, mode, out_len):
+    _check_mode(mode)
+    _require_cuda_f32(low, "sfb1d")
+    if low.dim() != 3:
+        raise IndexError("b200wave::sfb1d expects 3-D (N, C, L) tensors, got %d-D" % low.dim())
+    if high is not None:
+        _require_cuda_f32(high, "sfb1d")
+        if high.shape != low.shape:
+            raise RuntimeError("b200wave::sfb1d: low %s and high %s must have the same shape"
+                               % (tuple(low.shape), tuple(high.shape)))
+    lib = _cabi.load()
+    N, C, m = low.shape
+    full = idwt_len(m, len(g0), mode)
+    n = full if out_len < 0 else out_len
+    y = torch.empty((N, C, n), device=low.device, dtype=torch.float32)
+    if y.numel() == 0:
+        return y
+    lk, rs = _rows_view(low)
+    hk = None if high is None else high.contiguous()
+    a0, _ = _cabi.taps_array(g0)
+    a1, _ = _cabi.taps_array(g1)
+    with torch.cuda.device(low.device):
+        rc = lib.b200w_sfb1d_f32(lk.data_ptr(), rs, None if hk is None else hk.data_ptr(), N * C, m, a0, a1, len(g0),
+                                 int(mode), n, y.data_ptr(), _stream())
+    _cabi.check(rc, _mode_name(mode))
+    return y
+
+
+def _sfb1d_fake(low, high, g0, g1, mode, out_len):
+    N, C, m = low.shape
+    return low.new_empty((N, C, idwt_len(m, len(g0), mode) if out_len < 0 else out_len))
+
+
+def _afb1d_setup(ctx, inputs, output):
+    x, h0, h1, mode = inputs
+    ctx.taps = (h0, h1)
+    ctx.mode = mode
+    ctx.n = x.shape[-1]                      # AFB1D saves only the length (lowlevel.py:398)
+    ctx.set_materialize_grads(False)
+
+
+def _afb1d_backward(ctx, dlo, dhi):
+    dx = None
+    if ctx.needs_input_grad[0]:
+        if dlo is None and dhi is None:
+            return None, None, None, None
+        if dlo is None:
+            dlo = torch.zeros_like(dhi)
+        # synthesis with the saved analysis taps, cropped to the forward input (lowlevel.py:417-422)
+        dx = torch.ops.b200wave.sfb1d(dlo, dhi, ctx.taps[0], ctx.taps[1], ctx.mode, ctx.n)
+    return dx, None, None, None
+
+
+def _sfb1d_setup(ctx, inputs, output):
+    low, high, g0, g1, mode, out_len = inputs
+    ctx.taps = (g0, g1)
+    ctx.mode = mode
+    ctx.has_high = high is not None
+    ctx.cropped = output.shape[-1] != idwt_len(low.shape[-1], len(g0), mode)
+
+
+def _sfb1d_backward(ctx, dy):
+    dlo = dhi = None
+    need_lo = ctx.needs_input_grad[0]
+    need_hi = ctx.has_high and ctx.needs_input_grad[1]
+    if need_lo or need_hi:
+        if ctx.cropped:
+            raise RuntimeError("b200wave::sfb1d: backward through a cropped synthesis is not defined "
+                               "(the crop only exists inside AFB1D.backward)")
+        # analysis of dy with the un-reversed synthesis taps as correlators (lowlevel.py:736-742)
+        dlo, dhi = torch.ops.b200wave.afb1d(dy, ctx.taps[0], ctx.taps[1], ctx.mode)
+        if not need_lo:
+            dlo = None
+        if not need_hi:
+            dhi = None
+    return dlo, dhi, None, None, None, None
+
+
 # ------------------------------------------------------------------------------------------- ssim
 def _ssim_common(img1, img2, win, name):
     _require_cuda_f32(img1, name)
@@ -580,6 +702,8 @@ _LIB.impl("idwt2", _idwt2_cuda, "CUDA")
 _LIB.impl("ssim_fwd", _ssim_fwd_cuda, "CUDA")
 _LIB.impl("ssim_bwd", _ssim_bwd_cuda, "CUDA")
 _LIB.impl("afb2d_select", _afb2d_select_cuda, "CUDA")
+_LIB.impl("afb1d", _afb1d_cuda, "CUDA")
+_LIB.impl("sfb1d", _sfb1d_cuda, "CUDA")
 
 
 def _cpu_refuse(name):
@@ -589,7 +713,7 @@ def _cpu_refuse(name):
     return impl
 
 
-for _name in ("afb2d", "afb2d_select", "sfb2d", "dwt2", "idwt2", "ssim_fwd", "ssim_bwd"):
+for _name in ("afb2d", "afb2d_select", "sfb2d", "dwt2", "idwt2", "ssim_fwd", "ssim_bwd", "afb1d", "sfb1d"):
     _LIB.impl(_name, _cpu_refuse(_name), "CPU")
 
 torch.library.register_fake("b200wave::afb2d", _afb2d_fake, lib=_LIB)
@@ -598,6 +722,10 @@ torch.library.register_fake("b200wave::afb2d_select", _afb2d_select_fake, lib=_L
 torch.library.register_autograd("b200wave::afb2d_select", _afb2d_select_backward, setup_context=_afb2d_select_setup,
                                 lib=_LIB)
 torch.library.register_fake("b200wave::dwt2", _dwt2_fake, lib=_LIB)
+torch.library.register_fake("b200wave::afb1d", _afb1d_fake, lib=_LIB)
+torch.library.register_fake("b200wave::sfb1d", _sfb1d_fake, lib=_LIB)
+torch.library.register_autograd("b200wave::afb1d", _afb1d_backward, setup_context=_afb1d_setup, lib=_LIB)
+torch.library.register_autograd("b200wave::sfb1d", _sfb1d_backward, setup_context=_sfb1d_setup, lib=_LIB)
 torch.library.register_fake("b200wave::idwt2", _idwt2_fake, lib=_LIB)
 torch.library.register_fake("b200wave::ssim_fwd", _ssim_fwd_fake, lib=_LIB)
 torch.library.register_fake("b200wave::ssim_bwd", _ssim_bwd_fake, lib=_LIB)
@@ -612,6 +740,8 @@ dwt2 = torch.ops.b200wave.dwt2
 idwt2 = torch.ops.b200wave.idwt2
 ssim_fwd = torch.ops.b200wave.ssim_fwd
 ssim_bwd = torch.ops.b200wave.ssim_bwd
+afb1d = torch.ops.b200wave.afb1d
+sfb1d = torch.ops.b200wave.sfb1d
 
 
 def ssim_bench_kernels(sets, win):

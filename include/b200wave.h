@@ -22,6 +22,7 @@
  *   b200w_dwt_coeff_len pywt.dwt_coeff_len as called at pw/dwt/lowlevel.py:153
  *   b200w_freq_mask_c64 / b200w_abs_sign_f32 / b200w_sign_mul_f32
  *                       utils.py:71-117  Gaussian low / high pass in the Fourier domain
+ *   b200w_afb1d_f32 / b200w_sfb1d_f32             pw/dwt/lowlevel.py:368-424, 697-743  AFB1D / SFB1D
  *   b200w_tv_fwd_f32 / b200w_tv_bwd_f32           model.py:17-33  TVLoss
  *   b200w_phase_sums_c64 / b200w_phase_grad_c64   model.py:36-58  phase_consistency_loss
  *
@@ -217,6 +218,21 @@ int b200w_tv_fwd_f32(const float* x, int planes, int H, int W, void* workspace, 
                      float* out2, void* stream);
 int b200w_tv_bwd_f32(const float* x, const float* grad_out, float ch, float cw, int planes, int H, int W,
                      float* dx, void* stream);
+
+/*
+ * 1-D analysis / synthesis banks, SURVEY.md 8f row 3: the bodies of AFB1D.forward / SFB1D.forward
+ * (pw/dwt/lowlevel.py:389-405, 719-730 = afb1d / sfb1d of :91-172, :226-271 on an (N, C, 1, L) view) and, with the other
+ * bank's taps, of each other's backward (:407-424, :732-743).  `rows` = N*C signals.
+ * b200w_afb1d_f32: x (rows, n) with row stride x_rs -> lo, hi dense (rows, b200w_dwt_coeff_len(n, L, mode)); taps as the
+ *   module stores them (prep_filt_afb1d: already time-reversed).
+ * b200w_sfb1d_f32: lo (rows, m) with row stride lo_rs (the 'unpad' view of DWT1DInverse, transform1d.py:110-112, is
+ *   free), hi dense (rows, m) or NULL (= zeros) -> y dense (rows, out_len), out_len <= b200w_idwt_len(m, L, mode)
+ *   (the crop of AFB1D.backward, :421-422).
+ */
+int b200w_afb1d_f32(const float* x, int64_t x_rs, int rows, int n, const float* h0, const float* h1, int L, int mode,
+                    float* lo, float* hi, void* stream);
+int b200w_sfb1d_f32(const float* lo, int64_t lo_rs, const float* hi, int rows, int m, const float* g0, const float* g1,
+                    int L, int mode, int out_len, float* y, void* stream);
 
 /*
  * phase_consistency_loss, model.py:36-58 (constructed at train.py:94), SURVEY.md 8f row 4: minus the cosine
