@@ -110,3 +110,17 @@ def load_phase_cases():
         case["id"] = "%02d-%s" % (i, "x".join(str(d) for d in case["x"].shape))
         cases.append(case)
     return cases
+
+
+def load_dwt1d_cases():
+    z = np.load(os.path.join(GOLDEN, "dwt1d_cases.npz"))
+    cases = []
+    for i in range(int(z["ncases"])):
+        pre = "d%02d/" % i
+        case = {k[len(pre):]: z[k] for k in z.files if k.startswith(pre)}
+        case["J"] = int(case["J"])
+        case["mode"] = str(case["mode"])
+        case["wave"] = str(case["wave"])
+        case["id"] = "%02d-%s-J%d-%s-%d" % (i, case["wave"], case["J"], case["mode"], case["x"].shape[-1])
+        cases.append(case)
+    return cases

@@ -14,8 +14,8 @@ import torch
 import b200wave
 from b200wave import lowlevel
 from oracle import dwt_oracle, freq_oracle, fsd_oracle, ssim_oracle, tv_oracle
-from helpers import (RTOL_F32, case_filters, load_dwt_cases, load_freq_cases, load_fsd_cases, load_ssim_cases,
-                     load_phase_cases, load_tv_cases, rel_err)
+from helpers import (RTOL_F32, case_filters, load_dwt1d_cases, load_dwt_cases, load_freq_cases, load_fsd_cases,
+                     load_phase_cases, load_ssim_cases, load_tv_cases, rel_err)
 
 pytestmark = pytest.mark.gpu
 
@@ -721,6 +721,82 @@ def test_golden_tv_loss(case):
     assert abs(loss.item() - case["loss"]) <= RTOL_F32 * abs(case["loss"])
     loss.backward()
     assert rel_err(x.grad.cpu(), case["dx"]) < RTOL_F32
+
+
+DWT1D_CASES = load_dwt1d_cases()
+
+
+@pytest.mark.parametrize("case", DWT1D_CASES, ids=[c["id"] for c in DWT1D_CASES])
+def test_golden_dwt1d_forward_inverse_backward(case):
+    """b200wave.DWT1DForward / DWT1DInverse vs the unmodified reference (transform1d.py): coefficients, reconstruction,
+    the input gradient (AFB1D.backward chain) and the coefficient gradients (SFB1D.backward chain)."""
+    J, mode = case["J"], case["mode"]
+    xfm = b200wave.DWT1DForward(J=J, wave=(case["h0"][::-1].copy(), case["h1"][::-1].copy()), mode=mode).to(DEV)
+    ifm = b200wave.DWT1DInverse(wave=(case["g0"], case["g1"]), mode=mode).to(DEV)
+    assert np.allclose(xfm.h0.flatten().cpu().numpy(), case["h0"]) and tuple(xfm.h0.shape) == (1, 1, len(case["h0"]))
+    x = cu(case["x"], grad=True)
+    yl, yh = xfm(x)
+    assert yl.is_contiguous() and all(t.is_contiguous() for t in yh) and len(yh) == J
+    assert rel_err(yl.detach().cpu(), case["yl"]) < RTOL_F32
+    for j in range(J):
+        assert rel_err(yh[j].detach().cpu(), case["yh%d" % j]) < RTOL_F32
+    (dx,) = torch.autograd.grad([yl] + list(yh), x, [cu(case["gl"])] + [cu(case["gh%d" % j]) for j in range(J)])
+    assert rel_err(dx.cpu(), case["dx"]) < RTOL_F32
+    cl = cu(case["yl"], grad=True)
+    ch = [cu(case["yh%d" % j], grad=True) for j in range(J)]
+    rec = ifm((cl, ch))
+    assert rec.is_contiguous() and rel_err(rec.detach().cpu(), case["rec"]) < RTOL_F32
+    grads = torch.autograd.grad(rec, [cl] + ch, cu(case["gy"]))
+    assert rel_err(grads[0].cpu(), case["dcl"]) < RTOL_F32
+    for j in range(J):
+        assert rel_err(grads[1 + j].cpu(), case["dch%d" % j]) < RTOL_F32
+
+
+@pytest.mark.parametrize("wave", ["haar", "db4", "db8"])
+@pytest.mark.parametrize("mode", ["zero", "symmetric", "reflect", "periodic", "periodization"])
+def test_oracle_dwt1d_long_signals(wave, mode):
+    """Long odd-length signals (many CTAs, interior fast path + both border paths), every padding mode, against the
+    oracle; perfect reconstruction; absent detail bands = zeros; strided (non-contiguous) input rows."""
+    rng = np.random.default_rng(len(wave) * 7 + len(mode))
+    xn = rng.standard_normal((3, 2, 100003)).astype(np.float32)
+    xfm = b200wave.DWT1DForward(J=3, wave=wave, mode=mode).to(DEV)
+    ifm = b200wave.DWT1DInverse(wave=wave, mode=mode).to(DEV)
+    h0, h1 = (xfm.h0.flatten().cpu().numpy().astype(np.float64), xfm.h1.flatten().cpu().numpy().astype(np.float64))
+    g0, g1 = (ifm.g0.flatten().cpu().numpy().astype(np.float64), ifm.g1.flatten().cpu().numpy().astype(np.float64))
+    yl, yh = xfm(cu(xn))
+    lo = xn.astype(np.float64)
+    for j in range(3):
+        lo, hi = dwt_oracle.afb1d(lo, h0, h1, mode)
+        assert rel_err(yh[j].cpu(), hi) < RTOL_F32
+    assert rel_err(yl.cpu(), lo) < RTOL_F32
+    rec = ifm((yl, yh))
+    if mode in ("periodization",):
+        assert rec.shape[-1] == xn.shape[-1] + 1          # odd length: the reference returns the even extension
+    assert rel_err(rec[..., :xn.shape[-1]].cpu(), xn) < RTOL_F32
+    r = lo
+    for j in range(2, -1, -1):
+        z = np.zeros_like(yh[j].cpu().numpy(), dtype=np.float64)
+        if r.shape[-1] > z.shape[-1]:
+            r = r[..., :-1]
+        r = dwt_oracle.sfb1d(r, z, g0, g1, mode)
+    rec0 = ifm((yl, [None, None, None]))
+    if rec0.shape == r.shape:      # without detail bands the reference applies no 'unpad' (transform1d.py:106-112)
+        assert rel_err(rec0.cpu(), r) < RTOL_F32
+    xs = cu(np.ascontiguousarray(np.repeat(xn, 2, axis=-1)))[..., ::2]      # sample stride 2 -> copied, same result
+    yl2, _ = xfm(xs)
+    assert torch.equal(yl2, yl)
+    xr = cu(np.concatenate([xn, xn], axis=-1))[..., :xn.shape[-1]]          # row stride != length: taken as a view
+    yl3, _ = xfm(xr)
+    assert torch.equal(yl3, yl)
+
+
+def test_dwt1d_error_behaviour():
+    with pytest.raises(ValueError, match="Unkown pad type"):
+        b200wave.DWT1DForward(mode="constant")(cu(np.zeros((1, 1, 16), np.float32)))
+    with pytest.raises(AssertionError):
+        b200wave.DWT1DForward()(cu(np.zeros((1, 1, 4, 4), np.float32)))
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        b200wave.DWT1DForward()(torch.zeros(1, 1, 16))
 
 
 PHASE_CASES = load_phase_cases()

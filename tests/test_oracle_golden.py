@@ -182,3 +182,43 @@ def test_phase_loss_host_logic_without_gpu():
     crit = b200wave.phase_consistency_loss()
     with pytest.raises(RuntimeError, match="CUDA-only"):
         crit(torch.rand(1, 1, 8, 8), torch.rand(1, 1, 8, 8))
+
+
+DWT1D_CASES = __import__("helpers").load_dwt1d_cases()
+
+
+@pytest.mark.parametrize("case", DWT1D_CASES, ids=[c["id"] for c in DWT1D_CASES])
+def test_dwt1d_oracle_vs_reference(case):
+    """dwt_oracle.afb1d / sfb1d chained as DWT1DForward / DWT1DInverse do (transform1d.py:37-62, 93-115) and as their
+    backward passes do (lowlevel.py:407-424, 732-743) vs the unmodified reference's outputs and gradients."""
+    J, mode = case["J"], case["mode"]
+    h0, h1, g0, g1 = case["h0"], case["h1"], case["g0"], case["g1"]
+    lo = case["x"]
+    lens = []
+    for j in range(J):
+        lens.append(lo.shape[-1])
+        lo, hi = dwt_oracle.afb1d(lo, h0, h1, mode)
+        assert rel_err(hi, case["yh%d" % j]) < 1e-12
+    assert rel_err(lo, case["yl"]) < 1e-12
+    # AFB1D.backward chain: synthesis with the analysis taps, cropped to each level's input length
+    d = case["gl"]
+    for j in range(J - 1, -1, -1):
+        d = dwt_oracle.sfb1d(d, case["gh%d" % j], h0, h1, mode)[..., :lens[j]]
+    assert rel_err(d, case["dx"]) < 1e-12
+    # inverse + SFB1D.backward chain
+    r = case["yl"]
+    unpads = []
+    for j in range(J - 1, -1, -1):
+        hi = case["yh%d" % j]
+        unpads.append(r.shape[-1] > hi.shape[-1])
+        if unpads[-1]:
+            r = r[..., :-1]
+        r = dwt_oracle.sfb1d(r, hi, g0, g1, mode)
+    assert rel_err(r, case["rec"]) < 1e-12
+    g = case["gy"]
+    for j in range(J):
+        g, dhi = dwt_oracle.afb1d(g, g0, g1, mode)
+        assert rel_err(dhi, case["dch%d" % j]) < 1e-12
+        if unpads[J - 1 - j]:                       # autograd through x0[..., :-1]: a zero is appended
+            g = np.concatenate([g, np.zeros(g.shape[:-1] + (1,))], axis=-1)
+    assert rel_err(g, case["dcl"]) < 1e-12
