@@ -16,7 +16,7 @@ there is no CPU path.
 from . import ops  # noqa: F401  (registers torch.ops.b200wave.*)
 from . import dwt  # noqa: F401
 from .dwt import lowlevel  # noqa: F401
-from .dwt.transform2d import DWTForward, DWTInverse
+from .dwt.transform2d import DWTForward, DWTInverse, SWTForward
 from .dwt.transform1d import DWT1DForward, DWT1DInverse
 from .ssim import SSIM, ssim
 from .wavelets import Wavelet, wavelist  # noqa: F401
@@ -35,6 +35,6 @@ IDWT2D = IDWT
 DWT1D = DWT1DForward
 IDWT1D = DWT1DInverse
 
-__all__ = ["DWTForward", "DWTInverse", "DWT", "IDWT", "DWT2D", "IDWT2D", "DWT1DForward", "DWT1DInverse", "DWT1D", "IDWT1D",
+__all__ = ["DWTForward", "DWTInverse", "DWT", "IDWT", "DWT2D", "IDWT2D", "DWT1DForward", "DWT1DInverse", "DWT1D", "IDWT1D", "SWTForward",
            "SSIM", "ssim", "lowlevel",
            "Wavelet", "wavelist", "HostPipeline", "TVLoss", "phase_consistency_loss", "__version__"]

@@ -52,6 +52,8 @@ SYMBOLS = {
     "b200w_tv_bwd_f32": (_i, [_vp, _vp, ctypes.c_float, ctypes.c_float, _i, _i, _i, _vp, _vp]),
     "b200w_afb1d_f32": (_i, [_vp, _i64, _i, _i, _c_float_p, _c_float_p, _i, _i, _vp, _vp, _vp]),
     "b200w_sfb1d_f32": (_i, [_vp, _i64, _vp, _i, _i, _c_float_p, _c_float_p, _i, _i, _i, _vp, _vp]),
+    "b200w_swt2d_fwd_f32": (_i, [_vp, _i, _i, _i, _c_float_p, _c_float_p, _c_float_p, _c_float_p, _i, _i, _i, _vp, _vp]),
+    "b200w_swt2d_bwd_f32": (_i, [_vp, _i, _i, _i, _c_float_p, _c_float_p, _c_float_p, _c_float_p, _i, _i, _i, _vp, _vp]),
     "b200w_phase_workspace_bytes": (_sz, [_i, _i, _i]),
     "b200w_phase_sums_c64": (_i, [_vp, _vp, _i, _i, _i, ctypes.c_float, _vp, _sz, _vp, _vp]),
     "b200w_phase_grad_c64": (_i, [_vp, _vp, _i, _i, _i, ctypes.c_float, _vp, _vp, ctypes.c_float, _vp, _vp, _vp]),

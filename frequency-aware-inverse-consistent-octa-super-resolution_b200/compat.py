@@ -32,7 +32,7 @@ def install(force=False):
     pw.__version__ = "1.3.0+b200wave." + b200wave.__version__
     pw.__path__ = []
     for name in ("DWTForward", "DWTInverse", "DWT", "IDWT", "DWT2D", "IDWT2D", "DWT1DForward", "DWT1DInverse", "DWT1D",
-                 "IDWT1D"):
+                 "IDWT1D", "SWTForward"):
         setattr(pw, name, getattr(b200wave, name))
     dwt = types.ModuleType("pytorch_wavelets.dwt")
     dwt.__b200wave_alias__ = True

@@ -118,6 +118,23 @@ class SFB1D(object):
         return ops.sfb1d(low, high, _as_taps(g0, False), _as_taps(g1, False), int(mode), -1)
 
 
+def afb2d_atrous(x, filts, mode="periodization", dilation=1):
+    """One undecimated 2-D analysis level (pw/dwt/lowlevel.py:475-521): x (N, C, H, W) -> (N, 4C, H, W), channel
+    4c + 2a + e = (W filter a, then H filter e) of input channel c -- what the reference's two grouped convolutions
+    return (its docstring promises (N, C, 4, H, W); ``y.view(N, C, 4, H, W)`` is that).  ``filts`` = (h0, h1) or
+    (h0_col, h1_col, h0_row, h1_row), arrays or prepped tensors.  The reference's default mode ``'periodization'`` is
+    unknown to ``mypad`` and raises ``ValueError("Unkown pad type")`` there; so it does here."""
+    if len(filts) == 2:
+        filts = (filts[0], filts[1], filts[0], filts[1])
+    elif len(filts) != 4:
+        raise ValueError("Unknown form for input filts")
+    h0_col, h1_col, h0_row, h1_row = filts
+    if mode in ("per", "periodization") or mode not in _MODES:
+        raise ValueError("Unkown pad type: {}".format(mode))
+    return ops.swt2d(x, _as_taps(h0_row, True), _as_taps(h1_row, True), _as_taps(h0_col, True), _as_taps(h1_col, True),
+                     mode_to_int(mode), int(dilation))
+
+
 def _four_filters(filts, prep, device=None):
     """Normalise the ``filts`` argument of afb2d / sfb2d to (col_lo, col_hi, row_lo, row_hi) tensors.
     A pair means "same filters on both axes"; raw arrays go through ``prep``; prepared tensors are

@@ -91,3 +91,38 @@ class DWTInverse(nn.Module):
             yh = yh[:-ops.MAX_LEVELS]
             ll = ops.IDWT2Function.apply(taps[0], taps[1], taps[2], taps[3], mode, ll, *chunk)
         return ll
+
+
+class SWTForward(nn.Module):
+    """2-D stationary (undecimated) wavelet transform, drop-in for ``pw/dwt/transform2d.py:151-212``: same constructor
+    arguments and buffers; ``forward(x)`` returns a list of J tensors.  Each level is one launch of the a-trous kernel
+    (``csrc/swt.cu``) with dilation 2**j.
+
+    What the reference actually does (and this module reproduces): ``afb2d_atrous`` returns (N, 4C, H, W) -- not the
+    (N, C, 4, H, W) of its docstring -- so with J = 1 that is the shape of the single coefficient tensor; its default
+    mode ``'periodization'`` raises ``ValueError("Unkown pad type")`` inside ``mypad``; and for J > 1 its
+    ``ll = y[:, :, 0]`` slices a row of the 4-D tensor and the next level fails.  Here J > 1 follows the documented
+    intent instead: the next level's input is the (lo, lo) band of every channel.
+    """
+
+    def __init__(self, J=1, wave="db1", mode="periodization"):
+        super().__init__()
+        h0_col, h1_col, h0_row, h1_row = _filters_from(wave, ("dec_lo", "dec_hi"))
+        filts = lowlevel.prep_filt_afb2d(h0_col, h1_col, h0_row, h1_row)
+        self.register_buffer("h0_col", filts[0])
+        self.register_buffer("h1_col", filts[1])
+        self.register_buffer("h0_row", filts[2])
+        self.register_buffer("h1_row", filts[3])
+        self.J = J
+        self.mode = mode
+
+    def forward(self, x):
+        ll = x
+        coeffs = []
+        filts = (self.h0_col, self.h1_col, self.h0_row, self.h1_row)
+        for j in range(self.J):
+            y = lowlevel.afb2d_atrous(ll, filts, self.mode, 2 ** j)
+            coeffs.append(y)
+            n, c4, h, w = y.shape
+            ll = y.view(n, c4 // 4, 4, h, w)[:, :, 0]
+        return coeffs

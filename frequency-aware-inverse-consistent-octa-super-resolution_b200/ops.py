@@ -35,6 +35,9 @@ _LIB.define("idwt2(Tensor yl, Tensor?[] yh, int[] hw, float[] w_lo, float[] w_hi
             "int[] out_hw) -> Tensor")
 _LIB.define("afb1d(Tensor x, float[] h0, float[] h1, int mode) -> (Tensor, Tensor)")
 _LIB.define("sfb1d(Tensor low, Tensor? high, float[] g0, float[] g1, int mode, int out_len) -> Tensor")
+_LIB.define("swt2d(Tensor x, float[] w_lo, float[] w_hi, float[] h_lo, float[] h_hi, int mode, int dilation) -> Tensor")
+_LIB.define("swt2d_adjoint(Tensor dy, float[] w_lo, float[] w_hi, float[] h_lo, float[] h_hi, int mode, int dilation) "
+            "-> Tensor")
 _LIB.define("ssim_fwd(Tensor img1, Tensor img2, float[] win, bool size_average, int n_maps) -> (Tensor, Tensor)")
 _LIB.define("ssim_bwd(Tensor img1, Tensor img2, Tensor maps, Tensor grad_out, float[] win, bool size_average, "
             "bool need_d2) -> (Tensor, Tensor)")
@@ -611,6 +614,60 @@ def _sfb1d_backward(ctx, dy):
     return dlo, dhi, None, None, None, None
 
 
+# ------------------------------------------------------------------------------------------- a trous (SWT)
+def _check_swt_mode(mode):
+    if mode not in (0, 1, 4, 6):     # mypad: zero, symmetric, reflect, periodic (lowlevel.py:28-88)
+        raise ValueError("Unkown pad type: {}".format(_mode_name(mode)))
+
+
+def _swt_call(fn_name, t, w_lo, w_hi, h_lo, h_hi, mode, dilation, planes, H, W, out):
+    lib = _cabi.load()
+    if not (len(w_lo) == len(w_hi) == len(h_lo) == len(h_hi)):
+        raise RuntimeError("b200wave::swt2d: all four filters must have the same length")
+    a_wl, _ = _cabi.taps_array(w_lo)
+    a_wh, _ = _cabi.taps_array(w_hi)
+    a_hl, _ = _cabi.taps_array(h_lo)
+    a_hh, _ = _cabi.taps_array(h_hi)
+    with torch.cuda.device(t.device):
+        rc = getattr(lib, fn_name)(t.data_ptr(), planes, H, W, a_wl, a_wh, a_hl, a_hh, len(w_lo), int(dilation),
+                                   int(mode), out.data_ptr(), _stream())
+    _cabi.check(rc, _mode_name(mode))
+
+
+def _swt2d_cuda(x, w_lo, w_hi, h_lo, h_hi, mode, dilation):
+    _check_swt_mode(mode)
+    _require_cuda_f32(x, "swt2d")
+    if x.dim() != 4:
+        raise IndexError("b200wave::swt2d expects a 4-D (N, C, H, W) tensor, got %d-D" % x.dim())
+    N, C, H, W = x.shape
+    y = torch.empty((N, 4 * C, H, W), device=x.device, dtype=torch.float32)
+    if y.numel():
+        _swt_call("b200w_swt2d_fwd_f32", x.contiguous(), w_lo, w_hi, h_lo, h_hi, mode, dilation, N * C, H, W, y)
+    return y
+
+
+def _swt2d_adjoint_cuda(dy, w_lo, w_hi, h_lo, h_hi, mode, dilation):
+    _check_swt_mode(mode)
+    _require_cuda_f32(dy, "swt2d_adjoint")
+    N, C4, H, W = dy.shape
+    dx = torch.empty((N, C4 // 4, H, W), device=dy.device, dtype=torch.float32)
+    if dx.numel():
+        _swt_call("b200w_swt2d_bwd_f32", dy.contiguous(), w_lo, w_hi, h_lo, h_hi, mode, dilation, N * (C4 // 4), H, W, dx)
+    return dx
+
+
+def _swt2d_setup(ctx, inputs, output):
+    x, w_lo, w_hi, h_lo, h_hi, mode, dilation = inputs
+    ctx.args = (w_lo, w_hi, h_lo, h_hi, mode, dilation)
+
+
+def _swt2d_backward(ctx, dy):
+    dx = None
+    if ctx.needs_input_grad[0]:
+        dx = torch.ops.b200wave.swt2d_adjoint(dy, *ctx.args)
+    return dx, None, None, None, None, None, None
+
+
 # ------------------------------------------------------------------------------------------- ssim
 def _ssim_common(img1, img2, win, name):
     _require_cuda_f32(img1, name)
@@ -703,6 +760,8 @@ _LIB.impl("ssim_fwd", _ssim_fwd_cuda, "CUDA")
 _LIB.impl("ssim_bwd", _ssim_bwd_cuda, "CUDA")
 _LIB.impl("afb2d_select", _afb2d_select_cuda, "CUDA")
 _LIB.impl("afb1d", _afb1d_cuda, "CUDA")
+_LIB.impl("swt2d", _swt2d_cuda, "CUDA")
+_LIB.impl("swt2d_adjoint", _swt2d_adjoint_cuda, "CUDA")
 _LIB.impl("sfb1d", _sfb1d_cuda, "CUDA")
 
 
@@ -713,7 +772,8 @@ def _cpu_refuse(name):
     return impl
 
 
-for _name in ("afb2d", "afb2d_select", "sfb2d", "dwt2", "idwt2", "ssim_fwd", "ssim_bwd", "afb1d", "sfb1d"):
+for _name in ("afb2d", "afb2d_select", "sfb2d", "dwt2", "idwt2", "ssim_fwd", "ssim_bwd", "afb1d", "sfb1d", "swt2d",
+              "swt2d_adjoint"):
     _LIB.impl(_name, _cpu_refuse(_name), "CPU")
 
 torch.library.register_fake("b200wave::afb2d", _afb2d_fake, lib=_LIB)
@@ -723,6 +783,11 @@ torch.library.register_autograd("b200wave::afb2d_select", _afb2d_select_backward
                                 lib=_LIB)
 torch.library.register_fake("b200wave::dwt2", _dwt2_fake, lib=_LIB)
 torch.library.register_fake("b200wave::afb1d", _afb1d_fake, lib=_LIB)
+torch.library.register_fake("b200wave::swt2d", lambda x, wl, wh, hl, hh, mode, d:
+                            x.new_empty((x.shape[0], 4 * x.shape[1], x.shape[2], x.shape[3])), lib=_LIB)
+torch.library.register_fake("b200wave::swt2d_adjoint", lambda dy, wl, wh, hl, hh, mode, d:
+                            dy.new_empty((dy.shape[0], dy.shape[1] // 4, dy.shape[2], dy.shape[3])), lib=_LIB)
+torch.library.register_autograd("b200wave::swt2d", _swt2d_backward, setup_context=_swt2d_setup, lib=_LIB)
 torch.library.register_fake("b200wave::sfb1d", _sfb1d_fake, lib=_LIB)
 torch.library.register_autograd("b200wave::afb1d", _afb1d_backward, setup_context=_afb1d_setup, lib=_LIB)
 torch.library.register_autograd("b200wave::sfb1d", _sfb1d_backward, setup_context=_sfb1d_setup, lib=_LIB)
@@ -741,6 +806,7 @@ idwt2 = torch.ops.b200wave.idwt2
 ssim_fwd = torch.ops.b200wave.ssim_fwd
 ssim_bwd = torch.ops.b200wave.ssim_bwd
 afb1d = torch.ops.b200wave.afb1d
+swt2d = torch.ops.b200wave.swt2d
 sfb1d = torch.ops.b200wave.sfb1d
 
 

@@ -23,6 +23,7 @@
  *   b200w_freq_mask_c64 / b200w_abs_sign_f32 / b200w_sign_mul_f32
  *                       utils.py:71-117  Gaussian low / high pass in the Fourier domain
  *   b200w_afb1d_f32 / b200w_sfb1d_f32             pw/dwt/lowlevel.py:368-424, 697-743  AFB1D / SFB1D
+ *   b200w_swt2d_fwd_f32 / b200w_swt2d_bwd_f32     pw/dwt/lowlevel.py:175-223, 475-521  afb2d_atrous / SWTForward (8f row 3)
  *   b200w_tv_fwd_f32 / b200w_tv_bwd_f32           model.py:17-33  TVLoss
  *   b200w_phase_sums_c64 / b200w_phase_grad_c64   model.py:36-58  phase_consistency_loss
  *
@@ -233,6 +234,20 @@ int b200w_afb1d_f32(const float* x, int64_t x_rs, int rows, int n, const float* 
                     float* lo, float* hi, void* stream);
 int b200w_sfb1d_f32(const float* lo, int64_t lo_rs, const float* hi, int rows, int m, const float* g0, const float* g1,
                     int L, int mode, int out_len, float* y, void* stream);
+
+/*
+ * Undecimated (a trous) 2-D analysis bank, SURVEY.md 8f row 3: afb2d_atrous (pw/dwt/lowlevel.py:475-521, afb1d_atrous
+ * :175-223 along W then along H) = one level of SWTForward (pw/dwt/transform2d.py:151-212), and its adjoint.
+ * b200w_swt2d_fwd_f32: x dense (planes, H, W) -> y dense (planes, 4, H, W), band order (W-filter, H-filter) =
+ *   (lo,lo), (lo,hi), (hi,lo), (hi,hi) -- the channel order of the reference's two grouped convolutions; taps as stored
+ *   by prep_filt_afb2d (time-reversed), `w_*` along W (the reference's h*_row), `h_*` along H (h*_col); `dilation` = 2^level.
+ *   Modes: zero, symmetric, reflect, periodic (mypad has no 'periodization': B200W_ERR_BAD_MODE, as the reference raises).
+ * b200w_swt2d_bwd_f32: dx = adjoint applied to dy (planes, 4, H, W) -- what autograd derives from mypad + F.conv2d.
+ */
+int b200w_swt2d_fwd_f32(const float* x, int planes, int H, int W, const float* w_lo, const float* w_hi,
+                        const float* h_lo, const float* h_hi, int L, int dilation, int mode, float* y, void* stream);
+int b200w_swt2d_bwd_f32(const float* dy, int planes, int H, int W, const float* w_lo, const float* w_hi,
+                        const float* h_lo, const float* h_hi, int L, int dilation, int mode, float* dx, void* stream);
 
 /*
  * phase_consistency_loss, model.py:36-58 (constructed at train.py:94), SURVEY.md 8f row 4: minus the cosine

@@ -124,3 +124,16 @@ def load_dwt1d_cases():
         case["id"] = "%02d-%s-J%d-%s-%d" % (i, case["wave"], case["J"], case["mode"], case["x"].shape[-1])
         cases.append(case)
     return cases
+
+
+def load_swt_cases():
+    z = np.load(os.path.join(GOLDEN, "swt_cases.npz"))
+    cases = []
+    pres = sorted({k.split("/")[0] for k in z.files if "/" in k})
+    for pre in pres:
+        case = {k[len(pre) + 1:]: z[k] for k in z.files if k.startswith(pre + "/")}
+        case["mode"], case["wave"], case["dilation"] = str(case["mode"]), str(case["wave"]), int(case["dilation"])
+        case["id"] = "%s-%s-%s-d%d-%dx%d" % (pre, case["wave"], case["mode"], case["dilation"], case["x"].shape[-2],
+                                             case["x"].shape[-1])
+        cases.append(case)
+    return cases

@@ -15,7 +15,7 @@ import b200wave
 from b200wave import lowlevel
 from oracle import dwt_oracle, freq_oracle, fsd_oracle, ssim_oracle, tv_oracle
 from helpers import (RTOL_F32, case_filters, load_dwt1d_cases, load_dwt_cases, load_freq_cases, load_fsd_cases,
-                     load_phase_cases, load_ssim_cases, load_tv_cases, rel_err)
+                     load_phase_cases, load_ssim_cases, load_swt_cases, load_tv_cases, rel_err)
 
 pytestmark = pytest.mark.gpu
 
@@ -797,6 +797,52 @@ def test_dwt1d_error_behaviour():
         b200wave.DWT1DForward()(cu(np.zeros((1, 1, 4, 4), np.float32)))
     with pytest.raises(RuntimeError, match="CUDA-only"):
         b200wave.DWT1DForward()(torch.zeros(1, 1, 16))
+
+
+SWT_CASES = load_swt_cases()
+
+
+@pytest.mark.parametrize("case", SWT_CASES, ids=[c["id"] for c in SWT_CASES])
+def test_golden_swt_level(case):
+    """lowlevel.afb2d_atrous (one level of SWTForward) vs the unmodified reference function: output and the input
+    gradient autograd derives there (lowlevel.py:475-521)."""
+    from b200wave.dwt import lowlevel
+    filts = tuple(cu(case[k]) for k in ("h0_col", "h1_col", "h0_row", "h1_row"))
+    x = cu(case["x"], grad=True)
+    y = lowlevel.afb2d_atrous(x, filts, case["mode"], case["dilation"])
+    assert tuple(y.shape) == case["y"].shape and y.is_contiguous()
+    assert rel_err(y.detach().cpu(), case["y"]) < RTOL_F32
+    (dx,) = torch.autograd.grad(y, x, cu(case["gy"]))
+    assert rel_err(dx.cpu(), case["dx"]) < RTOL_F32
+
+
+@pytest.mark.parametrize("mode", ["zero", "symmetric", "reflect", "periodic"])
+def test_oracle_swt_forward_module(mode):
+    """SWTForward, J = 3 (dilations 1, 2, 4) on a BASELINE-sized plane against the oracle, and its gradient; J > 1
+    feeds the (lo, lo) band of every channel to the next level (the documented intent; the reference cannot run J > 1)."""
+    from oracle import swt_oracle
+    rng = np.random.default_rng(31)
+    xn = rng.standard_normal((2, 2, 304, 304)).astype(np.float32)
+    xfm = b200wave.SWTForward(J=3, wave="db2", mode=mode).to(DEV)
+    fl = [getattr(xfm, k).flatten().cpu().numpy().astype(np.float64) for k in ("h0_col", "h1_col", "h0_row", "h1_row")]
+    x = cu(xn, grad=True)
+    coeffs = xfm(x)
+    assert len(coeffs) == 3 and all(tuple(c.shape) == (2, 8, 304, 304) for c in coeffs)
+    ll = xn.astype(np.float64)
+    refs = []
+    for j in range(3):
+        y = swt_oracle.afb2d_atrous(ll, *fl, mode, 2 ** j)
+        refs.append(y)
+        assert rel_err(coeffs[j].detach().cpu(), y) < RTOL_F32
+        ll = y.reshape(2, 2, 4, 304, 304)[:, :, 0]
+    g = [rng.standard_normal(c.shape).astype(np.float32) for c in coeffs]
+    (dx,) = torch.autograd.grad(coeffs, x, [cu(t) for t in g])
+    d = np.zeros((2, 2, 304, 304))
+    for j in range(2, -1, -1):
+        gj = g[j].astype(np.float64).reshape(2, 2, 4, 304, 304).copy()
+        gj[:, :, 0] += d                      # the next level read this level's (lo, lo) band
+        d = swt_oracle.afb2d_atrous_backward(gj.reshape(2, 8, 304, 304), *fl, mode, 2 ** j)
+    assert rel_err(dx.cpu(), d) < RTOL_F32
 
 
 PHASE_CASES = load_phase_cases()

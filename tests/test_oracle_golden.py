@@ -1,9 +1,11 @@
 """CPU: the numpy oracle against the golden vectors produced by the unmodified reference
 (tests/golden/make_golden.py).  This is what pins the oracle."""
+import os
+
 import numpy as np
 import pytest
 
-from oracle import dwt_oracle, freq_oracle, fsd_oracle, phase_oracle, ssim_oracle, tv_oracle
+from oracle import dwt_oracle, freq_oracle, fsd_oracle, phase_oracle, ssim_oracle, swt_oracle, tv_oracle
 from helpers import (load_dwt_cases, load_freq_cases, load_fsd_cases, load_ssim_cases, load_tv_cases, case_filters,
                      rel_err)
 
@@ -222,3 +224,28 @@ def test_dwt1d_oracle_vs_reference(case):
         if unpads[J - 1 - j]:                       # autograd through x0[..., :-1]: a zero is appended
             g = np.concatenate([g, np.zeros(g.shape[:-1] + (1,))], axis=-1)
     assert rel_err(g, case["dcl"]) < 1e-12
+
+
+SWT_CASES = __import__("helpers").load_swt_cases()
+
+
+@pytest.mark.parametrize("case", SWT_CASES, ids=[c["id"] for c in SWT_CASES])
+def test_swt_oracle_vs_reference(case):
+    """swt_oracle.afb2d_atrous and its adjoint vs the unmodified reference function and autograd through it
+    (lowlevel.py:475-521)."""
+    fl = [case[k] for k in ("h0_col", "h1_col", "h0_row", "h1_row")]
+    assert rel_err(swt_oracle.afb2d_atrous(case["x"], *fl, case["mode"], case["dilation"]), case["y"]) < 1e-12
+    assert rel_err(swt_oracle.afb2d_atrous_backward(case["gy"], *fl, case["mode"], case["dilation"]), case["dx"]) < 1e-12
+
+
+def test_swt_host_logic_without_gpu():
+    """What the reference's SWTForward does with its default mode (recorded in the golden file) is what ours does:
+    ValueError("Unkown pad type: periodization") before any device work; CPU tensors are refused."""
+    import torch
+    import b200wave
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "swt_cases.npz"))
+    assert str(z["default_mode_error"]).startswith("ValueError: Unkown pad type: periodization")
+    with pytest.raises(ValueError, match="Unkown pad type: periodization"):
+        b200wave.SWTForward()(torch.zeros(1, 1, 8, 8))
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        b200wave.SWTForward(mode="zero")(torch.zeros(1, 1, 8, 8))
