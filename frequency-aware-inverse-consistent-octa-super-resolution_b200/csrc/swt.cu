@@ -25,29 +25,48 @@ struct SwtParams {
 
 __global__ void __launch_bounds__(kThreads) swt2d_fwd_kernel(const __grid_constant__ SwtParams p) {
     const size_t plane_px = (size_t)p.H * p.W;
-    const size_t total = plane_px * p.planes;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int k = (int)(idx % (unsigned)p.W);
-        const int i = (int)((idx / (unsigned)p.W) % (unsigned)p.H);
-        const size_t plane = idx / plane_px;
+    // planes on grid.y, pixels of a plane on grid.x with 32-bit index arithmetic (H * W < 2^31 is checked by the host)
+    for (int plane = blockIdx.y; plane < p.planes; plane += gridDim.y)
+    for (unsigned px = blockIdx.x * blockDim.x + threadIdx.x; px < (unsigned)plane_px; px += gridDim.x * blockDim.x) {
+        const int i = (int)(px / (unsigned)p.W);
+        const int k = (int)(px - (unsigned)i * (unsigned)p.W);
         const float* __restrict__ xp = p.in + plane * plane_px;
         float ll = 0.f, lh = 0.f, hl = 0.f, hh = 0.f;   // (row lo, col lo), (row lo, col hi), (row hi, col lo), (row hi, col hi)
-        for (int jh = 0; jh < p.L; ++jh) {
-            const int r = ext_index(i + p.d * jh - p.pl, p.H, p.mode);
-            if (r < 0) continue;
-            const float* __restrict__ xr = xp + (size_t)r * p.W;
-            float lo = 0.f, hi = 0.f;
-            for (int jw = 0; jw < p.L; ++jw) {
-                const int c = ext_index(k + p.d * jw - p.pl, p.W, p.mode);
-                if (c < 0) continue;
-                const float v = __ldg(xr + c);
-                lo = fmaf(p.w_lo[jw], v, lo);
-                hi = fmaf(p.w_hi[jw], v, hi);
+        const int r0 = i - p.pl, c0 = k - p.pl, span = p.d * (p.L - 1);
+        if (r0 >= 0 && r0 + span < p.H && c0 >= 0 && c0 + span < p.W) {      // interior window: no index maps
+            const float* __restrict__ xw = xp + (size_t)r0 * p.W + c0;
+            for (int jh = 0; jh < p.L; ++jh) {
+                const float* __restrict__ xr = xw + (size_t)(p.d * jh) * p.W;
+                float lo = 0.f, hi = 0.f;
+#pragma unroll 4
+                for (int jw = 0; jw < p.L; ++jw) {
+                    const float v = __ldg(xr + p.d * jw);
+                    lo = fmaf(p.w_lo[jw], v, lo);
+                    hi = fmaf(p.w_hi[jw], v, hi);
+                }
+                ll = fmaf(p.h_lo[jh], lo, ll);
+                lh = fmaf(p.h_hi[jh], lo, lh);
+                hl = fmaf(p.h_lo[jh], hi, hl);
+                hh = fmaf(p.h_hi[jh], hi, hh);
             }
-            ll = fmaf(p.h_lo[jh], lo, ll);
-            lh = fmaf(p.h_hi[jh], lo, lh);
-            hl = fmaf(p.h_lo[jh], hi, hl);
-            hh = fmaf(p.h_hi[jh], hi, hh);
+        } else {
+            for (int jh = 0; jh < p.L; ++jh) {
+                const int r = ext_index(r0 + p.d * jh, p.H, p.mode);
+                if (r < 0) continue;
+                const float* __restrict__ xr = xp + (size_t)r * p.W;
+                float lo = 0.f, hi = 0.f;
+                for (int jw = 0; jw < p.L; ++jw) {
+                    const int c = ext_index(c0 + p.d * jw, p.W, p.mode);
+                    if (c < 0) continue;
+                    const float v = __ldg(xr + c);
+                    lo = fmaf(p.w_lo[jw], v, lo);
+                    hi = fmaf(p.w_hi[jw], v, hi);
+                }
+                ll = fmaf(p.h_lo[jh], lo, ll);
+                lh = fmaf(p.h_hi[jh], lo, lh);
+                hl = fmaf(p.h_lo[jh], hi, hl);
+                hh = fmaf(p.h_hi[jh], hi, hh);
+            }
         }
         float* o = p.out + plane * 4 * plane_px + (size_t)i * p.W + k;
         o[0] = ll;
@@ -87,11 +106,10 @@ __device__ __forceinline__ int preimages(int s, int n, int pl, int pr, int mode,
 
 __global__ void __launch_bounds__(kThreads) swt2d_bwd_kernel(const __grid_constant__ SwtParams p) {
     const size_t plane_px = (size_t)p.H * p.W;
-    const size_t total = plane_px * p.planes;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)(idx % (unsigned)p.W);
-        const int r = (int)((idx / (unsigned)p.W) % (unsigned)p.H);
-        const size_t plane = idx / plane_px;
+    for (int plane = blockIdx.y; plane < p.planes; plane += gridDim.y)
+    for (unsigned px = blockIdx.x * blockDim.x + threadIdx.x; px < (unsigned)plane_px; px += gridDim.x * blockDim.x) {
+        const int r = (int)(px / (unsigned)p.W);
+        const int c = (int)(px - (unsigned)r * (unsigned)p.W);
         const float* __restrict__ g = p.in + plane * 4 * plane_px;
         int tr[kMaxPre], tc[kMaxPre];
         const int nr = preimages(r, p.H, p.pl, p.pr, p.mode, tr);
@@ -119,14 +137,15 @@ __global__ void __launch_bounds__(kThreads) swt2d_bwd_kernel(const __grid_consta
                 acc = fmaf(p.h_hi[jh], s_hi, acc);
             }
         }
-        p.out[idx] = acc;
+        p.out[plane * plane_px + px] = acc;
     }
 }
 
-static unsigned swt_grid(size_t n) {
-    size_t g = (n + kThreads - 1) / kThreads;
-    const size_t cap = 148 * 16;
-    return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+static dim3 swt_grid(int planes, size_t plane_px) {
+    unsigned gx = (unsigned)((plane_px + kThreads - 1) / kThreads);
+    unsigned gy = (unsigned)planes;
+    if (gy > 65535) gy = 65535;
+    return dim3(gx < 1 ? 1 : gx, gy, 1);
 }
 
 static int swt_fill(SwtParams& p, int planes, int H, int W, const float* w_lo, const float* w_hi, const float* h_lo,
@@ -135,7 +154,7 @@ static int swt_fill(SwtParams& p, int planes, int H, int W, const float* w_lo, c
     if (!(mode == B200W_MODE_ZERO || mode == B200W_MODE_SYMMETRIC || mode == B200W_MODE_REFLECT ||
           mode == B200W_MODE_PERIODIC))
         return B200W_ERR_BAD_MODE;   // mypad has no 'periodization' (pw/dwt/lowlevel.py:28-88)
-    if (planes < 1 || H < 1 || W < 1 || dilation < 1) return B200W_ERR_BAD_SHAPE;
+    if (planes < 1 || H < 1 || W < 1 || dilation < 1 || (long long)H * W > 0x7fffffffLL) return B200W_ERR_BAD_SHAPE;
     if (L < 1 || L > kMaxTaps) return B200W_ERR_BAD_TAPS;
     const int L2 = (L * dilation) / 2;
     p.pl = L2 - dilation;
@@ -166,7 +185,7 @@ extern "C" int b200w_swt2d_fwd_f32(const float* x, int planes, int H, int W, con
     if (rc) return rc;
     p.in = x;
     p.out = y;
-    swt2d_fwd_kernel<<<swt_grid((size_t)planes * H * W), kThreads, 0, (cudaStream_t)stream>>>(p);
+    swt2d_fwd_kernel<<<swt_grid(planes, (size_t)H * W), kThreads, 0, (cudaStream_t)stream>>>(p);
     note_launch("swt2d_fwd_kernel");
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? B200W_OK : set_last_cuda_error(e);
@@ -181,7 +200,7 @@ extern "C" int b200w_swt2d_bwd_f32(const float* dy, int planes, int H, int W, co
     if (rc) return rc;
     p.in = dy;
     p.out = dx;
-    swt2d_bwd_kernel<<<swt_grid((size_t)planes * H * W), kThreads, 0, (cudaStream_t)stream>>>(p);
+    swt2d_bwd_kernel<<<swt_grid(planes, (size_t)H * W), kThreads, 0, (cudaStream_t)stream>>>(p);
     note_launch("swt2d_bwd_kernel");
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? B200W_OK : set_last_cuda_error(e);

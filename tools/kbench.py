@@ -126,7 +126,49 @@ def fsd_case(n, h, w):
                 n, h, w, cs, t_f * 1e6, gbs, gbs / PEAK * 100, bytes_px, t_u * 1e6, t_u / t_f), flush=True)
 
 
+def dwt1d_case(rows, n, wave, mode):
+    """1-D analysis / synthesis level (AFB1D / SFB1D): 8 B per input sample in either direction."""
+    import b200wave
+    nsets = max(2, int(2 * 126e6 * 1.05 / (4 * rows * n)) + 1)
+    xs = [torch.randn(rows, 1, n, device=dev) for _ in range(nsets)]
+    xfm = b200wave.DWT1DForward(J=1, wave=wave, mode=mode).to(dev)
+    ifm = b200wave.DWT1DInverse(wave=wave, mode=mode).to(dev)
+    with torch.no_grad():
+        cs = [xfm(x) for x in xs]
+        t_a = timeit(lambda i: xfm(xs[i % nsets]), nsets)
+        t_s = timeit(lambda i: ifm(cs[i % nsets]), nsets)
+    b = 8.0 * rows * n
+    print("dwt1d %-5s %-13s %5dx%8d  afb1d %7.1f us %6.0f GB/s (%4.1f%%)   sfb1d %7.1f us %6.0f GB/s (%4.1f%%)" % (
+        wave, mode, rows, n, t_a * 1e6, b / t_a / 1e9, b / t_a / 1e9 / PEAK * 100, t_s * 1e6, b / t_s / 1e9,
+        b / t_s / 1e9 / PEAK * 100), flush=True)
+
+
+def swt_case(n, h, w, wave, mode, dilation):
+    """One undecimated level (afb2d_atrous): 4 B in + 16 B out per pixel."""
+    from b200wave.dwt import lowlevel
+    import b200wave
+    nsets = max(2, int(2 * 126e6 * 1.05 / (4 * n * h * w)) + 1)
+    xs = [torch.randn(n, 1, h, w, device=dev) for _ in range(nsets)]
+    m = b200wave.SWTForward(J=1, wave=wave, mode=mode).to(dev)
+    filts = (m.h0_col, m.h1_col, m.h0_row, m.h1_row)
+    with torch.no_grad():
+        t = timeit(lambda i: lowlevel.afb2d_atrous(xs[i % nsets], filts, mode, dilation), nsets)
+    b = 20.0 * n * h * w
+    print("swt   %-5s %-10s d=%d %4dx%4dx%4d  %7.1f us %6.0f GB/s (%4.1f%%)" % (
+        wave, mode, dilation, n, h, w, t * 1e6, b / t / 1e9, b / t / 1e9 / PEAK * 100), flush=True)
+
+
 what = (sys.argv[1] if len(sys.argv) > 1 else "all") if __name__ == "__main__" else "none"
+if what in ("dwt1d", "all"):
+    dwt1d_case(64, 1 << 20, "db3", "symmetric")
+    dwt1d_case(64, 1 << 20, "haar", "zero")
+    dwt1d_case(64, 1 << 20, "db8", "periodization")
+    dwt1d_case(4096, 4096, "db3", "symmetric")
+if what in ("swt", "all"):
+    swt_case(64, 304, 304, "db2", "symmetric", 1)
+    swt_case(64, 1024, 1024, "db2", "symmetric", 1)
+    swt_case(64, 1024, 1024, "db2", "periodic", 4)
+    swt_case(64, 1024, 1024, "haar", "zero", 1)
 if what in ("fsd", "all"):
     fsd_case(8, 256, 256)
     fsd_case(64, 256, 256)
