@@ -27,6 +27,9 @@
 #include <cstdlib>
 #include <type_traits>
 #include "dwt_tma.cuh"
+#ifndef B200W_EXP_PFD
+#define B200W_EXP_PFD 1      // prefetch distance of the level-0 consumer loop (experiments: -DB200W_EXP_PFD=n)
+#endif
 
 namespace b200w {
 
@@ -46,12 +49,16 @@ struct AfbT {
     // fixed ~1 us of issue + patch work on a sub-partition that is busy with consumer warps
     static constexpr int PS = kRotate ? 4 : (H2 == 1 ? 4 : (H2 == 4 ? 8 : 6));   // 2 * PS >= 2 * (L - 2): mirrored rows lie in the same stage
     static constexpr int SR = 2 * PS;                // rows per stage
-    static constexpr int NTC = L <= 6 ? 416 : (L <= 8 ? 352 : 256);   // consumer threads
-    static constexpr int MAXG = L <= 8 ? 5 : 4;      // row streams of the first level = service warps
+    // consumer threads.  db2 / db3: the cost model of the plan picks 3 row streams at the headline shapes (two busy warps
+    // per SM sub-partition), so 256 consumer threads suffice -- and a CTA of 352 threads may use up to 184 registers
+    // per thread, which the software-pipelined window loads of the level-0 loop need (measured: 18.6 -> 17.3 us at cfg2)
+    static constexpr int NTC = L == 2 ? 416 : (L <= 6 ? 256 : (L <= 8 ? 352 : 256));
+    static constexpr int MAXG = L == 2 ? 5 : (L <= 6 ? 3 : (L <= 8 ? 5 : 4));   // row streams of the first level = service warps
     static constexpr int NT = NTC + 32 * MAXG;
     // short filters keep their taps in registers: inside the (divergent) consumer branch the compiler cannot use
     // uniform-register / constant-bank operands and would otherwise re-load every tap for every row pair
     static constexpr bool kRegTaps = L <= 8;
+    static constexpr bool kPrefetch = L <= 6;        // software-pipelined window loads in the level-0 loop
 };
 
 // the taps of one kernel as a register-resident copy (same member names as TapsT)
@@ -284,13 +291,12 @@ __global__ void __launch_bounds__(AfbT<L, OFF>::NT, 1) afb_tma_kernel(const __gr
     const int G = l0.nseg;
     const unsigned bar_full = sbase + p.bar_off, bar_ready = bar_full + 8u * G * D, bar_empty = bar_ready + 8u * G * D;
 
-    // ---- set-up: this part's row / patch tables (built by the host, in the parameter block), barriers, the zero row ----
-    {
-        const int* const src = p.tab + part * p.tab_ints;
-        for (int i = tid; i < p.tab_ints; i += NT) tabs[i] = src[i];
-    }
-    const int nfix0 = mode != B200W_MODE_ZERO ? p.fix0_n : 0;
-    for (int i = tid; i < p.zrow_floats; i += NT) reinterpret_cast<float*>(smem + p.zrow_off)[i] = 0.f;
+    // ---- set-up, part 1: barriers; then the first two stages of every row stream go out BEFORE the tables are copied
+    //      (a regular box needs nothing but the parameter block), so the ~1 us of DRAM latency of the first tiles runs
+    //      under the rest of the set-up instead of in front of the consumers ----
+    constexpr int kProducerWarp = NTC / 32;   // the consumers are warps 0 .. NTC/32 - 1, then one service warp per stream
+    const int c0_0 = l0.c0[part], c1_0 = l0.c1[part];
+    const int nseg0 = (c1_0 - c0_0 + l0.R - 1) / l0.R;      // row streams of this part (<= G)
     if (tid < G * D) {
         mbar_init(bar_full + 8u * tid, 1);
         mbar_init(bar_ready + 8u * tid, 32);
@@ -301,18 +307,45 @@ __global__ void __launch_bounds__(AfbT<L, OFF>::NT, 1) afb_tma_kernel(const __gr
         tma_prefetch_map(&p.map_full);
         tma_prefetch_map(&p.map_row);
     }
+    __syncthreads();
+    const int early = (p.boxes != 0 && !(p.dbg & 8)) ? 2 : 0;   // stages issued here (0: the service warps issue them all)
+    if (early && warp >= kProducerWarp && lane == 0 && warp - kProducerWarp < nseg0) {
+        const int g = warp - kProducerWarp;
+        const int i0 = c0_0 + g * l0.R;
+        const int nst = (min(l0.R, c1_0 - i0) + H2 - 1 + PS - 1) / PS;
+        pdl_wait();      // the tiles read the input tensor (maybe the previous kernel's output)
+        for (int k = 0; k < min(early, nst); ++k) {
+            const unsigned full = bar_full + 8u * (g * D + k);
+            const unsigned dst = sbase + p.ring_off + (unsigned)(g * D + k) * stage_b;
+            mbar_expect_tx(full, stage_b);
+            B200W_CHK_S(dst, 16);
+            B200W_CHK_S(dst + stage_b - 16, 16);
+            for (int t = 0; t < nstrips; ++t)
+                tma_load_3d(dst + (unsigned)t * srbw4, &p.map_full, full, 4 * t * cps - hl, 2 * i0 - off + k * SR, plane);
+        }
+    }
+
+    // ---- set-up, part 2: this part's row / patch tables (built by the host, in the parameter block), the zero row ----
+    {
+        // The tables sit in the parameter block.  Indexing them per lane compiles to LDC with a lane-dependent offset,
+        // which the constant cache serialises address by address (32 passes per instruction: 1.3 us of set-up).  The
+        // address of a __grid_constant__ parameter is an ordinary generic address, so it is made opaque and read with
+        // coalesced loads through L1 / L2 instead.
+        const int* src = p.tab + part * p.tab_ints;
+        asm volatile("" : "+l"(src));
+        for (int i = tid; i < p.tab_ints; i += NT) tabs[i] = src[i];
+    }
+    const int nfix0 = mode != B200W_MODE_ZERO ? p.fix0_n : 0;
+    for (int i = tid; i < p.zrow_floats; i += NT) reinterpret_cast<float*>(smem + p.zrow_off)[i] = 0.f;
     pdl_wait();      // everything above used only the parameter block; from here on global memory is touched
     __syncthreads();
     TMA_MARK(2);
 
     const bool use_ready = mode != B200W_MODE_ZERO && nfix0 > 0;
-    const int c0_0 = l0.c0[part], c1_0 = l0.c1[part];
-    const int nseg0 = (c1_0 - c0_0 + l0.R - 1) / l0.R;      // row streams of this part (<= G)
     const int* const rt0 = tabs + l0.rtab_off;
     const int nrt0 = 2 * (c1_0 - c0_0) + L;
 
     // ================================ level 0: streamed through the ring ================================
-    constexpr int kProducerWarp = NTC / 32;   // the consumers are warps 0 .. NTC/32 - 1, then one service warp per stream
     if (warp >= kProducerWarp) {
         // ---- service warp of row stream g (all its lanes wait on the same barriers, so the hardware can put the warp
         // to sleep and wake it when the barrier completes).  Lane 0 issues the tiles of a stage into a free ring slot;
@@ -385,7 +418,7 @@ __global__ void __launch_bounds__(AfbT<L, OFF>::NT, 1) afb_tma_kernel(const __gr
             // the first two stages go out first, so that the consumers can start while the rest of the ring is filled
             SVC_MARK(48, 0);
             if (lane == 0)
-                for (int k = 0; k < min(2, nst); ++k) { issue(k); SVC_MARK(48, 1 + k); }
+                for (int k = early; k < min(2, nst); ++k) { issue(k); SVC_MARK(48, 1 + k); }
             __syncwarp();
             if (use_ready) { patch(0); SVC_MARK(24, 0); }
             if (lane == 0)
@@ -444,6 +477,27 @@ __global__ void __launch_bounds__(AfbT<L, OFF>::NT, 1) afb_tma_kernel(const __gr
                 if (!(p.dbg & 1)) mbar_wait(bar_wait + 8u * st, ph);
                 if (p.timeline && tid == 0 && k < 8) p.timeline[(size_t)blockIdx.x * 64 + 16 + k] = (unsigned long long)clock64();
                 if (!(p.dbg & 2))
+                if (C::kPrefetch) {   // the windows of row pair u + PFD are requested before row pair u is filtered
+                    constexpr int PFD = B200W_EXP_PFD < PS ? B200W_EXP_PFD : PS - 1;
+                    float v[PFD + 1][2][NE];
+#pragma unroll
+                    for (int u = 0; u < PFD; ++u) {
+                        B200W_CHK(rp + k * PS + u, 8);
+                        const int2 ro = rp[k * PS + u];
+                        afbt_load<L, OFF>(v[u], lane_ring + (unsigned)ro.x, lane_ring + (unsigned)ro.y);
+                    }
+#pragma unroll
+                    for (int u = 0; u < PS; ++u) {
+                        if (u + PFD < PS) {
+                            B200W_CHK(rp + k * PS + u + PFD, 8);
+                            const int2 rn = rp[k * PS + u + PFD];
+                            afbt_load<L, OFF>(v[(u + PFD) % (PFD + 1)], lane_ring + (unsigned)rn.x, lane_ring + (unsigned)rn.y);
+                        }
+                        afbt_pair<L, OFF>(taps, v[u % (PFD + 1)], acc, u % H2);
+                        afbt_store<L, OFF, false>(acc[kRotate ? 0 : (u + 1) % H2], o);
+                        afbt_rotate<L, OFF>(acc);
+                    }
+                } else
 #pragma unroll
                 for (int u = 0; u < PS; ++u) {
                     B200W_CHK(rp + k * PS + u, 8);
