@@ -6,20 +6,26 @@
 // taps as correlators -- the analysis passes of SFB2D.backward (pw/dwt/lowlevel.py:682-694).
 //
 // One CTA owns a horizontal part of one plane for all levels (rows a part needs from beyond its share are recomputed,
-// not exchanged).  Warp roles while the first level streams in from global memory:
-//   warp 0   producer: lane g feeds row stream g -- it waits for a free ring stage, arms the stage's mbarrier with the
-//            byte count and issues one cp.async.bulk.tensor per tile (SR full-width rows each; rows that the padding
-//            mode maps elsewhere -- symmetric / reflect / periodic extension above and below the image -- are fetched
-//            row by row from their source row; rows and columns outside the tensor are zero-filled by the engine)
-//   warp 1   patch warp: once a stage has landed it writes the extension columns left and right of the image rows
-//            (copies inside shared memory through a small table built once per CTA), then releases the stage to the
-//            consumers.  'zero' mode needs no patches: the consumers wait on the copy engine's barrier directly.
-//   warps 2+ consumers: a lane owns one pair of adjacent output columns of one row stream and marches down its rows:
-//            row pass in registers (4L FMAs per input row pair, taps from the constant bank), column pass scattered
-//            into a ring of L/2 pending output rows held as float2 (packed FFMA2), completed rows stored with 64-bit
-//            stores -- the three detail bands to global memory, the low-pass row into the CTA's shared-memory image.
-// Every lane reads its window with 128-bit shared loads at a fixed offset from the stage base: no border class, no
-// per-lane address arithmetic for the copies, no index maps in the loop.
+// not exchanged).  The first level is cut into G row streams (G <= MAXG, chosen by the plan); stream g owns a ring of D
+// stages of SR = 2 PS input rows.  Warp roles while the first level streams in from global memory:
+//   service warp g (warps NTC/32 ..): lane 0 waits for a free ring stage (`empty` mbarrier), arms the stage's `full`
+//            mbarrier with the byte count and issues ONE cp.async.bulk.tensor.3d per stage (box = SR full-width rows of
+//            the plane; rows and columns outside the tensor are zero-filled by the copy engine -- the 'zero' mode and
+//            every image border for free).  Stages whose rows the padding mode maps elsewhere in a non-monotonic way
+//            (wrapping modes) are fetched row by row from their source rows instead.  Once a stage has landed, all 32
+//            lanes write the extension columns left and right of the image rows (copies inside shared memory through a
+//            host-built table) and arrive on the stage's `ready` mbarrier.  'zero' mode needs no patches: the consumers
+//            wait on the copy engine's barrier directly.  The first two stages of every stream are issued in the
+//            prologue, before the tables are copied.
+//   consumer warps 0 .. NTC/32-1: a lane owns one pair of adjacent output columns of one row stream and marches down
+//            its rows: window loads one row pair ahead (register double buffer), row pass in registers (4L FMAs per
+//            input row pair), column pass scattered into a ring of L/2 pending output rows held as float2 (packed
+//            FFMA2), completed rows stored with 64-bit stores -- the three detail bands to global memory, the low-pass
+//            row into the CTA's shared-memory image (with its extension halo) -- then an arrive on `empty`.
+// Every lane reads its window with 128-bit shared loads at a host-precomputed per-pair offset from the stage base: no
+// border class, no per-lane address arithmetic for the copies, no index maps in the loop.  All row / offset / patch
+// tables are built by the host and travel in the parameter block; the prologue copies the part's share into shared
+// memory with coalesced generic loads.
 // The later levels read their input rows from the low-pass image of the level before (rows through a table of row
 // addresses, so the row extension costs nothing; extension columns written once per level by all threads).
 #include <algorithm>
