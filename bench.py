@@ -662,7 +662,9 @@ def main():
             if gbs:   # the step cannot be faster than its own copies at the box's measured duplex copy rate
                 bound_ms = max(h2d, d2h) / (gbs * 1e9) * 1e3
                 res["e2e"]["host_bound"] = {"duplex_gbs_per_rank_per_direction": gbs, "bound_ms_per_step": bound_ms,
-                                            "source": src}
+                                            "source": src,
+                                            "note": "probe taken on one box of the pool; boxes differ by +-30 % at "
+                                                    "N > 1, so a fraction above 1 means this box's host side is faster"}
                 res["e2e"]["frac_of_host_bound"] = bound_ms / (e2e_ms / e2e_steps)
             del pipe, host_in
         if rank == 0:
