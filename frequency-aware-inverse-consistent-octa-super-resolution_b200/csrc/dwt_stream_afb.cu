@@ -654,8 +654,9 @@ static int launch_afb_stream_t(AfbParams& p, int sms, cudaStream_t st) {
     // rows per work item of the first level.  Every item re-reads L/2 - 1 row pairs of warm-up, which favours long items
     // for long filters; short filters have (almost) no warm-up and balance better with short items.  Measured at
     // 64 x 1024^2 (B200W_STREAM_ROWS sweep, profiles/r02_notes.md): haar 6 / 16 rows = 81.5 / 85.8 us, db2 92.8 (8 rows:
-    // 94.1) / 104.7 us, db3 10 / 16 rows = 91.2 / 92.9 us, db4 and longer: 16+ rows stay best.
-    const int rpref = H2 == 1 ? 6 : (H2 == 2 ? 8 : (H2 == 3 ? 10 : std::max(16, 4 * (H2 - 1))));
+    // 94.1) / 104.7 us; db3 gains 2 % at J = 1 with 10 rows but loses 1-3 % in chains (J >= 2), so it keeps 16 like
+    // db4 and longer, where 16+ rows are best.
+    const int rpref = H2 == 1 ? 6 : (H2 == 2 ? 8 : std::max(16, 4 * (H2 - 1)));
     const long long slots = (long long)sms * C::MINB;
     long long base = 0;
     for (int j = 0; j < p.J; ++j) {
