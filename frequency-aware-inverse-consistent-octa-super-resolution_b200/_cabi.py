@@ -32,6 +32,7 @@ SSIM_MAX_WINDOW = 11
 
 # every symbol the header declares: name -> (restype, argtypes)
 _vp, _i, _i64, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t
+_c_double_p = ctypes.POINTER(ctypes.c_double)
 SYMBOLS = {
     "b200w_abi_version": (_i, []),
     "b200w_status_string": (ctypes.c_char_p, [_i]),
@@ -50,6 +51,10 @@ SYMBOLS = {
     "b200w_tv_workspace_bytes": (_sz, [_i, _i]),
     "b200w_tv_fwd_f32": (_i, [_vp, _i, _i, _i, _vp, _sz, _vp, _vp]),
     "b200w_tv_bwd_f32": (_i, [_vp, _vp, ctypes.c_float, ctypes.c_float, _i, _i, _i, _vp, _vp]),
+    "b200w_afb2d_f64": (_i, [_vp, _i64, _i64, _i, _i, _i, _c_double_p, _c_double_p, _i, _c_double_p, _c_double_p, _i,
+                             _i, _vp, _vp, _vp]),
+    "b200w_sfb2d_f64": (_i, [_vp, _i64, _i64, _vp, _i, _i, _i, _c_double_p, _c_double_p, _i, _c_double_p, _c_double_p, _i,
+                             _i, _vp, _i, _i, _vp]),
     "b200w_afb1d_f32": (_i, [_vp, _i64, _i, _i, _c_float_p, _c_float_p, _i, _i, _vp, _vp, _vp]),
     "b200w_sfb1d_f32": (_i, [_vp, _i64, _vp, _i, _i, _c_float_p, _c_float_p, _i, _i, _i, _vp, _vp]),
     "b200w_swt2d_fwd_f32": (_i, [_vp, _i, _i, _i, _c_float_p, _c_float_p, _c_float_p, _c_float_p, _i, _i, _i, _vp, _vp]),
@@ -136,6 +141,11 @@ def status_string(code):
 def taps_array(values):
     vals = [float(v) for v in values]
     return (ctypes.c_float * len(vals))(*vals), len(vals)
+
+
+def taps_array_f64(values):
+    vals = [float(v) for v in values]
+    return (ctypes.c_double * len(vals))(*vals), len(vals)
 
 
 def int_array(values):

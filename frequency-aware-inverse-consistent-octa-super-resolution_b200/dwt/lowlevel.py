@@ -12,7 +12,7 @@ import weakref
 import numpy as np
 import torch
 
-from .. import ops
+from .. import ops, ops64
 
 _MODES = {"zero": 0, "symmetric": 1, "per": 2, "periodization": 2, "constant": 3, "reflect": 4, "replicate": 5,
           "periodic": 6}
@@ -80,8 +80,9 @@ class AFB2D(object):
     @staticmethod
     def apply(x, h0_row, h1_row, h0_col, h1_col, mode):
         int_to_mode(mode)  # validates the code, ValueError("Unkown pad type") otherwise
-        return ops.afb2d(x, _as_taps(h0_row, True), _as_taps(h1_row, True),
-                         _as_taps(h0_col, True), _as_taps(h1_col, True), int(mode))
+        op = ops64.afb2d if x.dtype == torch.float64 else ops.afb2d
+        return op(x, _as_taps(h0_row, True), _as_taps(h1_row, True),
+                  _as_taps(h0_col, True), _as_taps(h1_col, True), int(mode))
 
 
 class SFB2D(object):
@@ -93,8 +94,9 @@ class SFB2D(object):
     @staticmethod
     def apply(low, highs, g0_row, g1_row, g0_col, g1_col, mode):
         int_to_mode(mode)
-        return ops.sfb2d(low, highs, _as_taps(g0_row, False), _as_taps(g1_row, False),
-                         _as_taps(g0_col, False), _as_taps(g1_col, False), int(mode), -1, -1)
+        op = ops64.sfb2d if low.dtype == torch.float64 else ops.sfb2d
+        return op(low, highs, _as_taps(g0_row, False), _as_taps(g1_row, False),
+                  _as_taps(g0_col, False), _as_taps(g1_col, False), int(mode), -1, -1)
 
 
 class AFB1D(object):

@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 
 from . import lowlevel
-from .. import ops
+from .. import ops, ops64
 from ..wavelets import as_wavelet, is_wavelet
 
 
@@ -26,6 +26,20 @@ def _filters_from(wave, attrs):
     if len(wave) == 4:
         return wave[0], wave[1], wave[2], wave[3]
     raise ValueError("wave must be a name, a Wavelet, or a tuple of 2 or 4 filters")
+
+
+def _is_f64(x, filt):
+    """Double inputs are served when the module's filters are double too (built under
+    ``torch.set_default_dtype(torch.float64)``, as the reference requires: with fp32 filters its conv raises)."""
+    if x.dtype != torch.float64:
+        if x.dtype == torch.float32 and filt.dtype == torch.float64:
+            raise RuntimeError("expected scalar type Double but found Float: the module holds float64 filters (built "
+                               "under torch.set_default_dtype(torch.float64)); pass double inputs, as with the reference")
+        return False
+    if filt.dtype != torch.float64:
+        raise RuntimeError("expected scalar type Float but found Double: the module holds float32 filters; build it "
+                           "under torch.set_default_dtype(torch.float64) for double inputs (as with the reference)")
+    return True
 
 
 class DWTForward(nn.Module):
@@ -57,6 +71,11 @@ class DWTForward(nn.Module):
         yh = []
         ll = x
         J = int(self.J)
+        if _is_f64(x, self.h0_col):   # the reference's double mode: level by level through the fp64 kernels
+            for _ in range(J):
+                ll, high = ops64.afb2d(ll, taps[0], taps[1], taps[2], taps[3], mode)
+                yh.append(high)
+            return ll, yh
         while J > 0:   # chunks of at most MAX_LEVELS levels per launch
             n = min(J, ops.MAX_LEVELS)
             outs = ops.DWT2Function.apply(ll, taps[0], taps[1], taps[2], taps[3], mode, n)
@@ -84,6 +103,15 @@ class DWTInverse(nn.Module):
         taps = [lowlevel.host_taps(f) for f in (self.g0_col, self.g1_col, self.g0_row, self.g1_row)]
         yh = list(yh)
         ll = yl
+        if _is_f64(yl, self.g0_col):   # double mode: pw/dwt/transform2d.py:134-148 level by level
+            for h in yh[::-1]:
+                if h is not None:
+                    if ll.shape[-2] > h.shape[-2]:
+                        ll = ll[..., :-1, :]
+                    if ll.shape[-1] > h.shape[-1]:
+                        ll = ll[..., :-1]
+                ll = ops64.sfb2d(ll, h, taps[0], taps[1], taps[2], taps[3], mode, -1, -1)
+            return ll
         # the loop over SFB2D.apply incl. the 'unpad' crop (a level reconstructed from an odd-sized input is one
         # sample too large, pw/dwt/transform2d.py:141-145) is one launch; the crop is a strided read
         while yh:

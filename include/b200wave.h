@@ -221,6 +221,19 @@ int b200w_tv_bwd_f32(const float* x, const float* grad_out, float ch, float cw, 
                      float* dx, void* stream);
 
 /*
+ * Double precision (the reference's fp64 mode: modules built under torch.set_default_dtype(torch.float64),
+ * pw tests/test_dwt.py:132-160): single-level banks with the signatures of b200w_afb2d_f32 / b200w_sfb2d_f32 on
+ * double data and double taps.  Simple one-thread-per-output kernels; the Python modules run multi-level fp64
+ * transforms level by level through them.
+ */
+int b200w_afb2d_f64(const double* x, int64_t x_plane_stride, int64_t x_row_stride, int planes, int H, int W,
+                    const double* w_lo, const double* w_hi, int Lw, const double* h_lo, const double* h_hi, int Lh,
+                    int mode, double* low, double* highs, void* stream);
+int b200w_sfb2d_f64(const double* low, int64_t low_plane_stride, int64_t low_row_stride, const double* highs, int planes,
+                    int h, int w, const double* w_lo, const double* w_hi, int Lw, const double* h_lo, const double* h_hi,
+                    int Lh, int mode, double* y, int out_h, int out_w, void* stream);
+
+/*
  * 1-D analysis / synthesis banks, SURVEY.md 8f row 3: the bodies of AFB1D.forward / SFB1D.forward
  * (pw/dwt/lowlevel.py:389-405, 719-730 = afb1d / sfb1d of :91-172, :226-271 on an (N, C, 1, L) view) and, with the other
  * bank's taps, of each other's backward (:407-424, :732-743).  `rows` = N*C signals.

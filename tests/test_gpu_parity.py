@@ -69,6 +69,67 @@ def test_golden_idwt_forward_backward(case):
         assert rel_err(grads[1 + j].cpu(), case["dch%d" % j]) < RTOL_F32
 
 
+@pytest.fixture
+def double_mode():
+    """The reference's fp64 mode: modules are built under torch.set_default_dtype(torch.float64) (tests/test_dwt.py:17-25)."""
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        yield
+    finally:
+        torch.set_default_dtype(old)
+
+
+RTOL_F64 = 1e-12      # double arithmetic against the float64 goldens (the reference itself was run in float64)
+
+
+@pytest.mark.parametrize("case", DWT_CASES, ids=[c["id"] for c in DWT_CASES])
+def test_golden_dwt_double(case, double_mode):
+    """The reference's `test_equal_double` mode (tests/test_dwt.py:132-160): float64 modules and inputs through the fp64
+    kernels against the float64 goldens -- forward, inverse and both gradient chains, at double precision."""
+    xfm, ifm = modules_for(case)
+    assert xfm.h0_col.dtype == torch.float64 and ifm.g0_col.dtype == torch.float64
+    J = case["J"]
+    dd = lambda a, grad=False: torch.tensor(np.asarray(a, dtype=np.float64), device=DEV, requires_grad=grad)
+    x = dd(case["x"], True)
+    yl, yh = xfm(x)
+    assert yl.dtype == torch.float64 and yl.is_contiguous() and all(h.is_contiguous() for h in yh)
+    assert rel_err(yl.detach().cpu(), case["yl"]) < RTOL_F64
+    for j in range(J):
+        assert rel_err(yh[j].detach().cpu(), case["yh%d" % j]) < RTOL_F64
+    (dx,) = torch.autograd.grad([yl] + list(yh), x, [dd(case["gyl"])] + [dd(case["gyh%d" % j]) for j in range(J)])
+    assert rel_err(dx.cpu(), case["dx"]) < RTOL_F64
+    cl = dd(case["yl"], True)
+    ch = [dd(case["yh%d" % j], True) for j in range(J)]
+    rec = ifm((cl, ch))
+    assert rec.dtype == torch.float64 and rel_err(rec.detach().cpu(), case["recon"]) < RTOL_F64
+    grads = torch.autograd.grad(rec, [cl] + ch, dd(case["grec"]))
+    assert rel_err(grads[0].cpu(), case["dcl"]) < RTOL_F64
+    for j in range(J):
+        assert rel_err(grads[1 + j].cpu(), case["dch%d" % j]) < RTOL_F64
+
+
+def test_double_mode_full_plane_and_mixed_dtypes(double_mode):
+    """A BASELINE-sized plane in double against the oracle (perfect reconstruction at 1e-12); fp32 input into fp64
+    modules and fp64 input into fp32 modules raise, as the reference's convolutions do."""
+    rng = np.random.default_rng(17)
+    xn = rng.standard_normal((2, 1, 304, 304))
+    xfm = b200wave.DWTForward(J=3, wave="db3", mode="symmetric").to(DEV)
+    ifm = b200wave.DWTInverse(wave="db3", mode="symmetric").to(DEV)
+    h = (xfm.h0_col.flatten().cpu().numpy(), xfm.h1_col.flatten().cpu().numpy())
+    x = torch.tensor(xn, device=DEV)
+    yl, yh = xfm(x)
+    oyl, oyh = dwt_oracle.dwt_forward(xn, 3, h, h, "symmetric")
+    assert rel_err(yl.cpu(), oyl) < RTOL_F64
+    for a, b in zip(yh, oyh):
+        assert rel_err(a.cpu(), b) < RTOL_F64
+    assert rel_err(ifm((yl, yh)).cpu(), xn) < 1e-11
+    rec0 = ifm((yl, [None, None, None]))
+    assert rec0.dtype == torch.float64
+    with pytest.raises(RuntimeError, match="expected scalar type"):
+        xfm(x.float())
+
+
 def _wave_taps(name):
     import pywt  # the stand-in (test infrastructure)
     w = pywt.Wavelet(name)
