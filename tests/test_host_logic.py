@@ -167,3 +167,17 @@ def test_backwards_are_marked_once_differentiable():
     from b200wave import ops, losses
     for fn in (ops.DWT2Function, ops.IDWT2Function, losses._TV, losses._PhaseCos):
         assert "once_differentiable" in inspect.getsource(fn)
+
+
+def test_tools_and_entry_points_parse():
+    """bench.py, __graft_entry__.py and every script under tools/ are syntactically valid (they only run on the GPU box)."""
+    import ast
+    import glob
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = glob.glob(os.path.join(root, "tools", "*.py")) + [os.path.join(root, "bench.py"),
+                                                              os.path.join(root, "__graft_entry__.py")]
+    assert len(files) > 10
+    for f in files:
+        with open(f) as fh:
+            ast.parse(fh.read(), filename=f)
