@@ -67,3 +67,20 @@ def sharded_ssim(ssim_module, img1, img2, group=None, reducer="mean", total_coun
     fused kernel, then the scalar means are combined (see ``global_mean`` for the gradient convention)."""
     local = ssim_module(img1, img2)
     return global_mean(local, img1.numel(), group=group, reducer=reducer, total_count=total_count)
+
+
+def average_gradients(params, group=None):
+    """Average the gradients of ``params`` over the ranks with ONE flat all-reduce (what DDP's reducer does for a
+    bucket), for training steps that DDP's per-forward bookkeeping does not fit -- the reference's step calls each
+    generator three times before one backward and never uses ``NetworkA2B.unet`` (train.py:170-240, model.py:249).
+    Parameters without a gradient are skipped (they must be the same on every rank).  No-op without a process group."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch._utils._flatten_dense_tensors(grads)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat /= dist.get_world_size(group)
+    for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+        g.copy_(f)

@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from b200wave.sharding import global_mean, shard_batch, shard_range
+from b200wave.sharding import average_gradients, global_mean, shard_batch, shard_range
 from oracle import ssim_oracle
 
 
@@ -81,6 +81,39 @@ def _ddp_worker(rank, world, port, n_batch, out_dir):
         np.save(os.path.join(out_dir, "ddp%d.npy" % rank), np.array([1.0]))
     finally:
         dist.destroy_process_group()
+
+
+def _avg_worker(rank, world, port, out_dir):
+    """average_gradients: one flat all-reduce equals the per-parameter mean over ranks; parameters that no rank used
+    (grad None) are skipped."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        gen = torch.Generator().manual_seed(5)
+        params = [torch.nn.Parameter(torch.rand(s, generator=gen, dtype=torch.float64)) for s in ((3, 4), (7,), (2, 2, 2))]
+        unused = torch.nn.Parameter(torch.zeros(5, dtype=torch.float64))
+        local = [torch.full_like(p, float(rank + 1)) * (i + 1) for i, p in enumerate(params)]
+        for p, g in zip(params, local):
+            p.grad = g.clone()
+        average_gradients(params + [unused])
+        mean_rank = sum(range(1, world + 1)) / world
+        for i, p in enumerate(params):
+            assert torch.allclose(p.grad, torch.full_like(p, mean_rank * (i + 1)), rtol=0, atol=1e-15)
+        assert unused.grad is None
+        np.save(os.path.join(out_dir, "avg%d.npy" % rank), np.array([1.0]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_average_gradients_flat_allreduce(tmp_path):
+    port = _free_port()
+    mp.spawn(_avg_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "avg0.npy").exists() and (tmp_path / "avg1.npy").exists()
+    p = torch.nn.Parameter(torch.ones(3))
+    p.grad = torch.ones(3)
+    average_gradients([p])                      # no process group: a no-op
+    assert torch.equal(p.grad, torch.ones(3))
 
 
 @pytest.mark.parametrize("n_batch", [4, 5])

@@ -124,15 +124,18 @@ def main():
     target_fake = torch.zeros(1, device=dev)
     buf_A, buf_B = utils.ReplayBuffer(), utils.ReplayBuffer()
 
-    def average_grads(params):
-        if world == 1:
-            return
-        grads = [p.grad for p in params if p.grad is not None]
-        flat = torch._utils._flatten_dense_tensors(grads)
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        flat /= world
-        for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-            g.copy_(f)
+    if args.impl == "b200wave":
+        from b200wave.sharding import average_gradients as average_grads   # one flat NCCL all-reduce per optimizer
+    else:   # the reference arm imports nothing of the package: the same flat all-reduce, restated
+        def average_grads(params):
+            if world == 1:
+                return
+            grads = [p.grad for p in params if p.grad is not None]
+            flat = torch._utils._flatten_dense_tensors(grads)
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            flat /= world
+            for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+                g.copy_(f)
 
     def split(img, hi, lo):          # train.py:173-176 and its three repeats
         hf = utils.high_pass(img[0], i=hi).unsqueeze(0).unsqueeze(0)
